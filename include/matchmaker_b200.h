@@ -1,0 +1,117 @@
+/*
+ * matchmaker_b200 -- C ABI of the B200-native interaction-scoring library.
+ *
+ * This is the drop-in boundary for the query-document interaction hot path of
+ * sebastian-hofstaetter/matchmaker.  The reference is pure Python/PyTorch and has no FFI of
+ * its own; each entry point below replaces the *inline arithmetic* of one reference method
+ * (cited as path:line relative to the reference repository root) and is what a binding for
+ * that method calls.  The Python host layer (matchmaker_b200/) binds these symbols with
+ * ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every function returns 0 (MMB200_OK) or a negative MMB200_ERR_* code;
+ *     mmb200_last_error() returns a thread-local human-readable message for the last failure;
+ *   - pointers whose name does not end in `_host` are DEVICE pointers valid on the CURRENT
+ *     CUDA device of the calling thread; `stream` is a cudaStream_t (0 = legacy default);
+ *     launches are asynchronous with respect to the host and ordered on `stream`;
+ *   - tensors are dense row-major ("contiguous" in PyTorch terms) unless a stride is given;
+ *   - the library never falls back to a CPU implementation: on a device that is not
+ *     compute capability 10.x every compute entry point fails with MMB200_ERR_UNSUPPORTED.
+ */
+#ifndef MATCHMAKER_B200_H_
+#define MATCHMAKER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMB200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define MMB200_API __attribute__((visibility("default")))
+#else
+#define MMB200_API
+#endif
+
+/* error codes */
+#define MMB200_OK 0
+#define MMB200_ERR_INVALID (-1)     /* bad argument (shape, dtype, alignment, null pointer) */
+#define MMB200_ERR_CUDA (-2)        /* a CUDA runtime / driver call failed */
+#define MMB200_ERR_UNSUPPORTED (-3) /* device is not sm_100, or shape outside kernel limits */
+
+/* element types of embedding / vector tensors */
+#define MMB200_F16 0
+#define MMB200_BF16 1
+#define MMB200_F32 2
+
+/* element types of mask tensors (nonzero = real token, zero = padding) */
+#define MMB200_MASK_NONE 0
+#define MMB200_MASK_U8 1  /* torch.bool / uint8 */
+#define MMB200_MASK_I32 2
+#define MMB200_MASK_I64 3 /* HF attention_mask */
+#define MMB200_MASK_F32 4 /* matchmaker `(tokens > 0).float()` masks */
+
+/* kernel selection for entry points that have more than one device implementation */
+#define MMB200_IMPL_AUTO 0
+#define MMB200_IMPL_SIMT 1    /* CUDA-core kernel, any shape/dtype */
+#define MMB200_IMPL_TCGEN05 2 /* TMA + tcgen05 tensor-core kernel (fails if shape unsupported) */
+
+MMB200_API int mmb200_version(void);
+MMB200_API const char* mmb200_last_error(void);
+
+/* Properties of CUDA device `device` (-1 = current). Any out pointer may be NULL. */
+MMB200_API int mmb200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * ColBERT late-interaction max-sim
+ *
+ *   score[p] = sum_{i < Lq, q_mask[qi][i]} max_{j < Ld} ( d_mask[di][j] ? <q[qi][i], d[di][j]> : -1000 )
+ *
+ * Replaces: ColBERT.forward scoring            matchmaker/models/colbert.py:68-75   (masks given)
+ *           ColBERT.forward_aggregation        matchmaker/models/colbert.py:100-112 (masks NULL)
+ *           ColBERT.forward_inbatch_aggregation matchmaker/models/colbert.py:154-162
+ *               (all pairs: n_pairs = n_q * n_d, pair_q[p] = p / n_d, pair_d[p] = p % n_d, or
+ *                mmb200_maxsim_allpairs_fwd below)
+ *
+ * q      [n_q, Lq, dim]  dtype `dtype`
+ * d      [n_d, Ld, dim]  dtype `dtype`
+ * q_mask [n_q, Lq] or NULL, d_mask [n_d, Ld] or NULL, element type `mask_dtype`
+ * pair_q / pair_d [n_pairs] int32 or NULL.  With NULL: qi = p / docs_per_query, di = p
+ *        (docs_per_query = 1 is the training/re-ranking case "pair p = query p x doc p";
+ *         docs_per_query = 1000 is BASELINE config 3 "1 query x 1000 docs").
+ * out    [n_pairs] float32
+ * argmax [n_pairs, Lq] int32 or NULL: index j* of the max per query token (-1 when the query
+ *        token is masked or every document position is masked) -- what backward needs.
+ * ------------------------------------------------------------------------------------------ */
+MMB200_API int mmb200_maxsim_fwd(const void* q, const void* d, const void* q_mask, const void* d_mask,
+                      const int32_t* pair_q, const int32_t* pair_d, float* out, int32_t* argmax,
+                      int64_t n_q, int64_t n_d, int64_t n_pairs, int32_t docs_per_query, int32_t Lq,
+                      int32_t Ld, int32_t dim, int32_t dtype, int32_t mask_dtype, int32_t impl,
+                      void* stream);
+
+/* Backward of mmb200_maxsim_fwd (pairs mode with pair_q = pair_d = NULL, docs_per_query >= 1).
+ * grad_out [n_pairs] f32; argmax from the forward; grad_q [n_q, Lq, dim] f32 and
+ * grad_d [n_d, Ld, dim] f32 are OVERWRITTEN (zero-filled then accumulated).
+ * Mirrors what autograd derives from colbert.py:68-75 (gradient flows only through the max
+ * element; masked query tokens and fully masked documents get none). */
+MMB200_API int mmb200_maxsim_bwd(const void* q, const void* d, const float* grad_out, const int32_t* argmax,
+                      float* grad_q, float* grad_d, int64_t n_q, int64_t n_d, int64_t n_pairs,
+                      int32_t docs_per_query, int32_t Lq, int32_t Ld, int32_t dim, int32_t dtype,
+                      void* stream);
+
+/* Host-buffer variant (the end-to-end call): all pointers are HOST pointers (pinned memory
+ * gives full PCIe bandwidth, pageable works).  Documents are streamed to the device in chunks
+ * on internal streams, overlapped with the kernel; scores are copied back before returning.
+ * Synchronous.  Same semantics as mmb200_maxsim_fwd with pair_q = pair_d = NULL. */
+MMB200_API int mmb200_maxsim_fwd_host(const void* q_host, const void* d_host, const void* q_mask_host,
+                           const void* d_mask_host, float* out_host, int64_t n_q, int64_t n_d,
+                           int32_t docs_per_query, int32_t Lq, int32_t Ld, int32_t dim, int32_t dtype,
+                           int32_t mask_dtype, int64_t chunk_pairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATCHMAKER_B200_H_ */

@@ -1,0 +1,26 @@
+// Internal interface of the max-sim kernels (shared by maxsim.cu and maxsim_host.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mmb {
+
+struct MaxsimParams {
+  const void* q;
+  const void* d;
+  const void* q_mask;
+  const void* d_mask;
+  const int32_t* pair_q;
+  const int32_t* pair_d;
+  float* out;
+  int32_t* argmax;
+  int64_t n_q, n_d, n_pairs;
+  int64_t pair_base;  // query of pair p (when pair_q == NULL) is (p + pair_base) / docs_per_query
+  int32_t docs_per_query, Lq, Ld, dim, mask_dtype;
+};
+
+// Validates, picks SIMT or tcgen05 and launches on `stream`.
+int maxsim_fwd_device(const MaxsimParams& P, int dtype, int impl, cudaStream_t stream);
+
+}  // namespace mmb

@@ -1,0 +1,164 @@
+"""Torch-facing wrappers of the interaction kernels (C ABI in ``include/matchmaker_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the current stream; the arithmetic runs in
+``libmatchmaker_b200.so``.  No function in this module has a CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float32: _lib.F32}
+_MASK_DTYPES = {torch.bool: _lib.MASK_U8, torch.uint8: _lib.MASK_U8, torch.int32: _lib.MASK_I32,
+                torch.int64: _lib.MASK_I64, torch.float32: _lib.MASK_F32}
+_IMPLS = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}
+
+
+def _require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.MatchmakerB200Error(
+                "matchmaker_b200 interaction ops run on CUDA (sm_100a) tensors only; got a "
+                f"{t.device} tensor and there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise _lib.MatchmakerB200Error(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _prep_mask(m: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if m is None:
+        return None
+    if m.dtype not in _MASK_DTYPES:
+        m = m != 0
+    return m.contiguous()
+
+
+def _common_mask_dtype(a: Optional[torch.Tensor], b: Optional[torch.Tensor]):
+    """Both masks of one call share one element type (one `mask_dtype` argument)."""
+    if a is not None and b is not None and a.dtype != b.dtype:
+        a, b = (a != 0), (b != 0)
+    code = _lib.MASK_NONE
+    for m in (a, b):
+        if m is not None:
+            code = _MASK_DTYPES[m.dtype]
+    return a, b, code
+
+
+def maxsim(q: torch.Tensor, d: torch.Tensor, q_mask: Optional[torch.Tensor] = None,
+           d_mask: Optional[torch.Tensor] = None, docs_per_query: int = 1,
+           pair_q: Optional[torch.Tensor] = None, pair_d: Optional[torch.Tensor] = None,
+           impl: str = "auto", return_argmax: bool = False):
+    """ColBERT max-sim scores, fp32.
+
+    q [n_q, Lq, dim], d [n_d, Ld, dim] (fp16 / bf16 / fp32, same dtype), masks [n, L] (nonzero =
+    token).  Pair p scores query ``pair_q[p]`` (default ``p // docs_per_query``) against document
+    ``pair_d[p]`` (default ``p``).  Semantics: matchmaker/models/colbert.py:68-75 / :100-112.
+    """
+    dev = _require_cuda(q, d, q_mask, d_mask, pair_q, pair_d)
+    if q.dtype != d.dtype or q.dtype not in _DTYPES:
+        raise _lib.MatchmakerB200Error(f"q/d must share a dtype in fp16/bf16/fp32, got {q.dtype}, {d.dtype}")
+    if q.dim() != 3 or d.dim() != 3 or q.shape[-1] != d.shape[-1]:
+        raise _lib.MatchmakerB200Error(f"expected q [n_q,Lq,dim], d [n_d,Ld,dim]; got {tuple(q.shape)}, {tuple(d.shape)}")
+    q = q.contiguous()
+    d = d.contiguous()
+    q_mask, d_mask, mcode = _common_mask_dtype(_prep_mask(q_mask), _prep_mask(d_mask))
+    n_q, Lq, dim = q.shape
+    n_d, Ld, _ = d.shape
+    if q_mask is not None and tuple(q_mask.shape) != (n_q, Lq):
+        raise _lib.MatchmakerB200Error("q_mask shape mismatch")
+    if d_mask is not None and tuple(d_mask.shape) != (n_d, Ld):
+        raise _lib.MatchmakerB200Error("d_mask shape mismatch")
+    if pair_q is not None or pair_d is not None:
+        if pair_q is None or pair_d is None:
+            raise _lib.MatchmakerB200Error("pair_q and pair_d must be given together")
+        pair_q = pair_q.to(torch.int32).contiguous()
+        pair_d = pair_d.to(torch.int32).contiguous()
+        n_pairs = pair_q.numel()
+        if pair_d.numel() != n_pairs:
+            raise _lib.MatchmakerB200Error("pair_q / pair_d length mismatch")
+    else:
+        n_pairs = n_d
+        if n_q * docs_per_query < n_d:
+            raise _lib.MatchmakerB200Error("n_q * docs_per_query < n_d")
+    out = torch.empty(n_pairs, dtype=torch.float32, device=dev)
+    argmax = torch.empty((n_pairs, Lq), dtype=torch.int32, device=dev) if return_argmax else None
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.mmb200_maxsim_fwd(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(pair_q), _ptr(pair_d),
+                                   _ptr(out), _ptr(argmax), n_q, n_d, n_pairs, docs_per_query, Lq, Ld, dim,
+                                   _DTYPES[q.dtype], mcode, _IMPLS[impl], _stream(dev))
+    _lib.check(rc, "mmb200_maxsim_fwd")
+    return (out, argmax) if return_argmax else out
+
+
+def maxsim_allpairs(q: torch.Tensor, q_mask: Optional[torch.Tensor], d: torch.Tensor,
+                    d_mask: Optional[torch.Tensor], impl: str = "auto") -> torch.Tensor:
+    """All query x document max-sim scores [n_q, n_d] (colbert.py:154-162)."""
+    n_q, n_d = q.shape[0], d.shape[0]
+    idx = torch.arange(n_q * n_d, device=q.device, dtype=torch.int32)
+    pq = torch.div(idx, n_d, rounding_mode="floor").to(torch.int32)
+    pd = (idx - pq * n_d).to(torch.int32)
+    return maxsim(q, d, q_mask, d_mask, pair_q=pq, pair_d=pd, impl=impl).view(n_q, n_d)
+
+
+def maxsim_bwd(q: torch.Tensor, d: torch.Tensor, grad_out: torch.Tensor, argmax: torch.Tensor,
+               docs_per_query: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Gradients of :func:`maxsim` (pairs mode) w.r.t. q and d, fp32."""
+    dev = _require_cuda(q, d, grad_out, argmax)
+    q = q.contiguous()
+    d = d.contiguous()
+    n_q, Lq, dim = q.shape
+    n_d, Ld, _ = d.shape
+    grad_out = grad_out.to(torch.float32).contiguous()
+    gq = torch.empty((n_q, Lq, dim), dtype=torch.float32, device=dev)
+    gd = torch.empty((n_d, Ld, dim), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.mmb200_maxsim_bwd(_ptr(q), _ptr(d), _ptr(grad_out), _ptr(argmax.contiguous()), _ptr(gq), _ptr(gd),
+                                   n_q, n_d, n_d, docs_per_query, Lq, Ld, dim, _DTYPES[q.dtype], _stream(dev))
+    _lib.check(rc, "mmb200_maxsim_bwd")
+    return gq, gd
+
+
+def maxsim_host(q: torch.Tensor, d: torch.Tensor, q_mask: Optional[torch.Tensor] = None,
+                d_mask: Optional[torch.Tensor] = None, docs_per_query: int = 1, chunk_pairs: int = 0,
+                device: Optional[torch.device] = None) -> torch.Tensor:
+    """End-to-end max-sim over HOST tensors (pinned for full PCIe rate): document slabs are streamed to the
+    GPU and scored while the next slab is in flight; returns a host fp32 tensor.  This is the call
+    dense_retrieval.py:398-412 would make for token matrices gathered from the CPU memmap storage."""
+    for t in (q, d, q_mask, d_mask):
+        if t is not None and t.is_cuda:
+            raise _lib.MatchmakerB200Error("maxsim_host takes host tensors; use maxsim() for device tensors")
+    if q.dtype != d.dtype or q.dtype not in _DTYPES:
+        raise _lib.MatchmakerB200Error("q/d must share a dtype in fp16/bf16/fp32")
+    q = q.contiguous()
+    d = d.contiguous()
+    q_mask, d_mask, mcode = _common_mask_dtype(_prep_mask(q_mask), _prep_mask(d_mask))
+    n_q, Lq, dim = q.shape
+    n_d, Ld, _ = d.shape
+    if n_q * docs_per_query < n_d:
+        raise _lib.MatchmakerB200Error("n_q * docs_per_query < n_d")
+    out = torch.empty(n_d, dtype=torch.float32, pin_memory=True)
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        rc = lib.mmb200_maxsim_fwd_host(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(out), n_q, n_d,
+                                        docs_per_query, Lq, Ld, dim, _DTYPES[q.dtype], mcode, chunk_pairs)
+    _lib.check(rc, "mmb200_maxsim_fwd_host")
+    return out

@@ -1,0 +1,167 @@
+"""Parity of the CUDA max-sim path (through the C ABI) with the oracle / golden vectors.
+Bar: <= 1e-3 relative fp32 (BASELINE.json north_star); fp16/bf16 inputs are upcast for the oracle so
+products are exact and only accumulation order differs."""
+import pytest
+import torch
+
+from conftest import assert_close_rel, load_golden
+from matchmaker_b200 import _lib, interaction
+from oracle import interaction_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _cuda(*ts):
+    return [None if t is None else t.to(DEV) for t in ts]
+
+
+def test_golden_small_fp32_masked_agg_allpairs():
+    g = load_golden("colbert_small")
+    q, d, qm, dm = _cuda(g["q"], g["d"], g["q_mask"], g["d_mask"])
+    assert_close_rel(interaction.maxsim(q, d, qm, dm), g["score"], what="forward")
+    assert_close_rel(interaction.maxsim(q, d), g["agg"], what="forward_aggregation")
+    assert_close_rel(interaction.maxsim_allpairs(q, qm, d, dm), g["allpairs"], what="inbatch")
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt", "auto"])
+def test_golden_cfg3_shape_fp16(impl):
+    g = load_golden("colbert_cfg3")
+    q, d, qm, dm = _cuda(g["q"], g["d"], g["q_mask"], g["d_mask"])
+    s = interaction.maxsim(q, d, qm, dm, docs_per_query=int(g["docs_per_query"]), impl=impl)
+    assert_close_rel(s, g["score"], what=f"cfg3 {impl}")
+
+
+SHAPES = [  # n_q, docs_per_query, Lq, Ld, dim, dtype
+    (5, 3, 32, 180, 128, torch.float16),
+    (3, 7, 17, 300, 64, torch.float16),     # KBS=1, 3 tiles, ragged Lq
+    (4, 2, 64, 57, 256, torch.bfloat16),    # NPAD=64, single tile
+    (2, 5, 128, 129, 192, torch.float16),   # NPAD=128 (512 TMEM cols), odd k-block count
+    (300, 1, 32, 180, 128, torch.float16),  # query changes every pair; more pairs than SMs
+    (1, 1, 1, 1, 64, torch.float16),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_seeded_vs_oracle(shape, impl):
+    n_q, dpq, Lq, Ld, dim, dt = shape
+    q, d, qm, dm = O.synth_colbert_inputs(n_q, dpq, Lq, Ld, dim, seed=99 + Lq + Ld, dtype=dt, full_q=False)
+    ref = O.maxsim_one_query_many_docs(q.float(), d.float(), qm, dm, dpq)
+    cq, cd, cqm, cdm = _cuda(q, d, qm, dm)
+    got = interaction.maxsim(cq, cd, cqm, cdm, docs_per_query=dpq, impl=impl)
+    assert_close_rel(got, ref, what=f"{shape} {impl}")
+    # unmasked aggregation (colbert.py:100-112)
+    ref2 = O.maxsim_one_query_many_docs(q.float(), d.float(), None, None, dpq)
+    assert_close_rel(interaction.maxsim(cq, cd, docs_per_query=dpq, impl=impl), ref2, what=f"{shape} {impl} nomask")
+
+
+@pytest.mark.parametrize("mdt", [torch.bool, torch.uint8, torch.int32, torch.int64, torch.float32, torch.float16])
+def test_mask_dtypes(mdt):
+    q, d, qm, dm = O.synth_colbert_inputs(3, 4, 32, 100, 128, seed=7, full_q=False)
+    ref = O.maxsim_one_query_many_docs(q.float(), d.float(), qm, dm, 4)
+    cq, cd = _cuda(q, d)
+    got = interaction.maxsim(cq, cd, qm.to(DEV).to(mdt), dm.to(DEV).to(mdt), docs_per_query=4)
+    assert_close_rel(got, ref, what=str(mdt))
+
+
+def test_fully_masked_doc_and_query_token_edge_cases():
+    q, d, qm, dm = O.synth_colbert_inputs(2, 3, 32, 180, 128, seed=11)
+    dm[1] = 0          # document with no real token: every position scores -1000
+    dm[4, 1:] = 0      # single-token document
+    qm[1, 5:] = 0
+    qm[0] = 0          # query with no real token: score 0
+    ref = O.maxsim_one_query_many_docs(q.float(), d.float(), qm, dm, 3)
+    cq, cd, cqm, cdm = _cuda(q, d, qm, dm)
+    for impl in ("tcgen05", "simt"):
+        assert_close_rel(interaction.maxsim(cq, cd, cqm, cdm, docs_per_query=3, impl=impl), ref, what=impl)
+    assert ref[3].item() == -1000.0 * 5
+
+
+def test_non_prefix_masks():
+    q, d, qm, dm = O.synth_colbert_inputs(2, 2, 32, 180, 128, seed=12)
+    g = torch.Generator().manual_seed(3)
+    dm = (torch.rand(dm.shape, generator=g) > 0.4).long()
+    qm = (torch.rand(qm.shape, generator=g) > 0.3).long()
+    ref = O.maxsim_one_query_many_docs(q.float(), d.float(), qm, dm, 2)
+    cq, cd, cqm, cdm = _cuda(q, d, qm, dm)
+    for impl in ("tcgen05", "simt"):
+        assert_close_rel(interaction.maxsim(cq, cd, cqm, cdm, docs_per_query=2, impl=impl), ref, what=impl)
+
+
+def test_pair_index_arrays_and_allpairs_fp16():
+    q, d, qm, dm = O.synth_colbert_inputs(6, 1, 32, 90, 128, seed=13, full_q=False)
+    ref = O.maxsim_allpairs(q.float(), qm, d.float(), dm)
+    cq, cd, cqm, cdm = _cuda(q, d, qm, dm)
+    for impl in ("tcgen05", "simt"):
+        assert_close_rel(interaction.maxsim_allpairs(cq, cqm, cd, cdm, impl=impl), ref, what=f"allpairs {impl}")
+    pq = torch.tensor([5, 0, 0, 3, 3, 3, 1], dtype=torch.int32, device=DEV)
+    pd = torch.tensor([0, 5, 2, 2, 4, 1, 1], dtype=torch.int32, device=DEV)
+    got = interaction.maxsim(cq, cd, cqm, cdm, pair_q=pq, pair_d=pd)
+    assert_close_rel(got, ref[pq.long().cpu(), pd.long().cpu()], what="gather pairs")
+
+
+def test_argmax_and_backward_vs_autograd():
+    q, d, qm, dm = O.synth_colbert_inputs(3, 2, 16, 40, 64, seed=14, dtype=torch.float32, full_q=False)
+    qr = q.clone().requires_grad_(True)
+    dr = d.clone().requires_grad_(True)
+    qe = qr.repeat_interleave(2, dim=0)
+    s = torch.bmm(qe, dr.transpose(2, 1))
+    s = s.masked_fill(~dm.bool().unsqueeze(1), -1000.0).max(-1).values
+    s = (s * qm.repeat_interleave(2, dim=0).float()).sum(-1)
+    g = torch.randn(s.shape, generator=torch.Generator().manual_seed(1))
+    s.backward(g)
+    from matchmaker_b200 import autograd
+    cq = q.to(DEV).requires_grad_(True)
+    cd = d.to(DEV).requires_grad_(True)
+    out = autograd.maxsim(cq, cd, qm.to(DEV), dm.to(DEV), docs_per_query=2)
+    assert_close_rel(out, s.detach(), what="fwd")
+    out.backward(g.to(DEV))
+    assert_close_rel(cq.grad, qr.grad, what="grad_q")
+    assert_close_rel(cd.grad, dr.grad, what="grad_d")
+
+
+def test_baseline_size_properties():
+    """BASELINE config 3 (64 queries x 1000 docs, Lq=32, Ld=180, dim=128, fp16): size-independent properties
+    -- tcgen05 == SIMT, permutation equivariance over documents, chunking invariance, oracle on a sample."""
+    n_q, dpq = 64, 1000
+    q, d, qm, dm = O.synth_colbert_inputs(n_q, dpq, 32, 180, 128, seed=1237)
+    cq, cd, cqm, cdm = _cuda(q, d, qm, dm)
+    s = interaction.maxsim(cq, cd, cqm, cdm, docs_per_query=dpq, impl="tcgen05")
+    assert s.shape == (n_q * dpq,) and torch.isfinite(s).all()
+    s_simt = interaction.maxsim(cq, cd, cqm, cdm, docs_per_query=dpq, impl="simt")
+    assert_close_rel(s, s_simt, what="tc vs simt")
+    # a document's score does not depend on where it sits in the batch
+    perm = torch.randperm(n_q * dpq, generator=torch.Generator().manual_seed(5)).to(DEV)
+    pq = torch.div(perm, dpq, rounding_mode="floor").to(torch.int32)
+    s_perm = interaction.maxsim(cq, cd, cqm, cdm, pair_q=pq, pair_d=perm.to(torch.int32), impl="tcgen05")
+    assert torch.equal(s_perm, s[perm])
+    # scoring a slice on its own gives the same numbers (bit-exact: same per-pair arithmetic)
+    lo, hi = 17 * dpq, 19 * dpq
+    s_slice = interaction.maxsim(cq[17:19], cd[lo:hi], cqm[17:19], cdm[lo:hi], docs_per_query=dpq, impl="tcgen05")
+    assert torch.equal(s_slice, s[lo:hi])
+    # oracle on 2 queries
+    ref = O.maxsim_one_query_many_docs(q[:2].float(), d[:2 * dpq].float(), qm[:2], dm[:2 * dpq], dpq)
+    assert_close_rel(s[:2 * dpq], ref, what="oracle sample")
+
+
+def test_host_buffer_pipeline_matches_device_path():
+    q, d, qm, dm = O.synth_colbert_inputs(4, 250, 32, 180, 128, seed=21)
+    ref = interaction.maxsim(*_cuda(q, d, qm, dm), docs_per_query=250)
+    got = interaction.maxsim_host(q.pin_memory(), d.pin_memory(), qm.pin_memory(), dm.pin_memory(),
+                                  docs_per_query=250, chunk_pairs=96)
+    assert not got.is_cuda
+    assert torch.equal(got, ref.cpu())
+    got2 = interaction.maxsim_host(q, d, None, None, docs_per_query=250)  # pageable, default chunking, no masks
+    assert torch.equal(got2, interaction.maxsim(*_cuda(q, d), docs_per_query=250).cpu())
+
+
+def test_invalid_arguments_raise():
+    q = torch.zeros(2, 32, 128, dtype=torch.float16, device=DEV)
+    d = torch.zeros(5, 180, 128, dtype=torch.float16, device=DEV)
+    with pytest.raises(_lib.MatchmakerB200Error):
+        interaction.maxsim(q, d)  # 2 queries x 1 doc/query < 5 docs
+    with pytest.raises(_lib.MatchmakerB200Error):
+        interaction.maxsim(q, d.float())
+    with pytest.raises(_lib.MatchmakerB200Error):
+        interaction.maxsim(q.float(), d.float(), docs_per_query=3, impl="tcgen05")  # fp32 has no tcgen05 path

@@ -1,0 +1,108 @@
+"""The oracle (oracle/interaction_oracle.py) against the golden vectors produced by the reference's own
+classes (tests/golden/*.npz, generator oracle/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import interaction_oracle as O
+
+
+def _eq(a, b, rtol=1e-6, atol=1e-7):
+    assert torch.allclose(a.double(), b.double(), rtol=rtol, atol=atol), (a - b).abs().max()
+
+
+@pytest.mark.parametrize("tag", ["small", "cfg1"])
+def test_knrm(tag):
+    g = load_golden(f"knrm_{tag}")
+    score, sec = O.kernel_pool_knrm(g["q"], g["d"], g["q_mask"], g["d_mask"], g["mu"], g["sigma"], g["weight"])
+    _eq(score, g["score"])
+    _eq(sec["per_kernel"], g["per_kernel"])
+    _eq(sec["cosine_matrix_masked"], g["cosine_matrix_masked"])
+    _eq(sec["query_mean_vector"], g["query_mean_vector"])
+
+
+@pytest.mark.parametrize("tag", ["k11", "k21"])
+def test_tk_interaction(tag):
+    g = load_golden(f"tk_{tag}")
+    score, sec = O.kernel_pool_tk(g["q_ctx"], g["d_ctx"], g["q_mask"], g["d_mask"], g["mu"], g["sigma"], g["alpha"],
+                                  g["weight"])
+    _eq(score, g["score"], 1e-5, 1e-6)
+    _eq(sec["per_kernel"], g["per_kernel"], 1e-5, 1e-5)
+    _eq(sec["cosine_matrix"], g["cosine_matrix"])
+
+
+@pytest.mark.parametrize("sat", ["embedding", "log"])
+def test_tkl_interaction(sat):
+    g = load_golden(f"tkl_{sat}")
+    params = {k[3:]: v for k, v in g.items() if k.startswith("p__")}
+    score, sec = O.tkl_interaction(g["q_ctx"], g["q_mask"], g["doc_chunks_ctx"], g["doc_chunk_mask"],
+                                   g["packed_indices"], int(g["chunk_pieces"]), params, sat)
+    _eq(score, g["score"], 1e-5, 1e-5)
+    _eq(sec["orig_score"], g["orig_score"], 1e-5, 1e-5)
+    assert torch.equal(sec["top_non_overlapping_idx"], g["top_non_overlapping_idx"])
+    _eq(sec["top_k_non_overlapping"], g["top_k_non_overlapping"], 1e-5, 1e-5)
+
+
+def test_tkl_chunking_matches_golden_packing():
+    g = load_golden("tkl_embedding")
+    cd2, cp2, packed, pieces = O.tkl_chunk_documents(g["d"], g["d_mask"])
+    assert torch.equal(packed, g["packed_indices"]) and pieces == int(g["chunk_pieces"])
+    assert torch.equal(cp2[packed][:, O.TKL_OVERLAP:-O.TKL_OVERLAP], g["doc_chunk_mask"])
+
+
+def test_colbert_small():
+    g = load_golden("colbert_small")
+    _eq(O.maxsim_pairs(g["q"].clone(), g["d"].clone(), g["q_mask"], g["d_mask"]), g["score"])
+    _eq(O.maxsim_pairs(g["q"].clone(), g["d"].clone(), None, None), g["agg"])
+    _eq(O.maxsim_allpairs(g["q"].clone(), g["q_mask"], g["d"].clone(), g["d_mask"]), g["allpairs"])
+
+
+def test_colbert_cfg3_shape():
+    g = load_golden("colbert_cfg3")
+    s = O.maxsim_one_query_many_docs(g["q"].float(), g["d"].float(), g["q_mask"], g["d_mask"], int(g["docs_per_query"]))
+    _eq(s, g["score"])
+
+
+def test_bert_dot():
+    g = load_golden("bert_dot_small")
+    _eq(O.dot_pairs(g["qv"], g["dv"]), g["score"])
+
+
+def test_flat_ip_known_answer():
+    # parity unpinned (faiss absent): hand-checkable known answer incl. the tie-break (score desc, id asc)
+    P = torch.tensor([[1., 0.], [0., 1.], [1., 0.], [2., 2.], [-1., 0.]])
+    ids = torch.tensor([50, 40, 30, 20, 10])
+    Q = torch.tensor([[1., 0.], [0., -1.]])
+    s, i = O.flat_ip_search(Q, P, ids, 3, chunk=2)
+    assert i.tolist() == [[20, 30, 50], [10, 30, 50]]
+    assert s.tolist() == [[2., 1., 1.], [0., 0., 0.]]
+    s, i = O.flat_ip_search(Q, P[:2], ids[:2], 3)
+    assert i[0].tolist() == [50, 40, -1]
+
+
+def test_flat_ip_matches_plain_topk():
+    q, p = O.synth_dense_inputs(7, 3000, 64, seed=5, dtype=torch.float32)
+    ids = torch.randperm(3000) + 100
+    s, i = O.flat_ip_search(q, p, ids, 10, chunk=700)
+    full = q @ p.T
+    ts, ti = torch.topk(full, 10, dim=1)
+    assert torch.equal(ts, s) and torch.equal(ids[ti], i)
+
+
+@pytest.mark.skipif(not __import__("oracle.reference_loader", fromlist=["x"]).reference_available(),
+                    reason="reference repo not mounted (GPU box)")
+def test_golden_regenerates_from_reference():
+    """When /root/reference is mounted, re-run the reference class and compare with the committed fixture."""
+    from oracle import reference_loader as R
+    g = load_golden("knrm_small")
+    ref = R.load_knrm(11)
+    with torch.no_grad():
+        ref.dense.weight.copy_(g["weight"].view(1, -1))
+        score = ref.forward(g["q"], g["d"], g["q_mask"], g["d_mask"])
+    _eq(score, g["score"])
+    cls, inst = R.load_colbert()
+    c = load_golden("colbert_small")
+    with torch.no_grad():
+        s = inst.forward({"vecs": c["q"].clone(), "attention_mask": c["q_mask"]},
+                         {"vecs": c["d"].clone(), "attention_mask": c["d_mask"]}, use_fp16=False)
+    _eq(s, c["score"])
