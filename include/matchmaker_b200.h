@@ -82,12 +82,15 @@ MMB200_API int mmb200_device_info(int device, int* sm_count, int* cc_major, int*
  * pair_q / pair_d [n_pairs] int32 or NULL.  With NULL: qi = p / docs_per_query, di = p
  *        (docs_per_query = 1 is the training/re-ranking case "pair p = query p x doc p";
  *         docs_per_query = 1000 is BASELINE config 3 "1 query x 1000 docs").
+ * pair_dmask [n_pairs] int32 or NULL: row of d_mask applied to pair p (default di).  Exists only
+ *        to reproduce colbert.py:158, which indexes the document mask by the QUERY position.
  * out    [n_pairs] float32
  * argmax [n_pairs, Lq] int32 or NULL: index j* of the max per query token (-1 when the query
  *        token is masked or every document position is masked) -- what backward needs.
  * ------------------------------------------------------------------------------------------ */
 MMB200_API int mmb200_maxsim_fwd(const void* q, const void* d, const void* q_mask, const void* d_mask,
-                      const int32_t* pair_q, const int32_t* pair_d, float* out, int32_t* argmax,
+                      const int32_t* pair_q, const int32_t* pair_d, const int32_t* pair_dmask,
+                      float* out, int32_t* argmax,
                       int64_t n_q, int64_t n_d, int64_t n_pairs, int32_t docs_per_query, int32_t Lq,
                       int32_t Ld, int32_t dim, int32_t dtype, int32_t mask_dtype, int32_t impl,
                       void* stream);
@@ -110,6 +113,45 @@ MMB200_API int mmb200_maxsim_fwd_host(const void* q_host, const void* d_host, co
                            const void* d_mask_host, float* out_host, int64_t n_q, int64_t n_d,
                            int32_t docs_per_query, int32_t Lq, int32_t Ld, int32_t dim, int32_t dtype,
                            int32_t mask_dtype, int64_t chunk_pairs);
+
+/* ------------------------------------------------------------------------------------------
+ * Cosine match matrix + RBF kernel pooling (KNRM / TK)
+ *
+ *   c_ij  = <q_i/(|q_i|+1e-13), d_j/(|d_j|+1e-13)>
+ *   S_ik  = sum_j d_mask[j] * exp(-(c_ij - mu_k)^2 / (2 sigma_k^2))
+ *   P_k   = sum_i q_mask[i] * log_scale * log(max(alpha_k * S_ik, 1e-10))
+ *   score = sum_k weight_k * P_k
+ *
+ * Replaces: KNRM.forward        matchmaker/models/knrm.py:52-84        (alpha = NULL, log_scale = 0.01)
+ *           ECAI20_TK.forward   matchmaker/models/published/ecai20_tk.py:105-124 (log_scale = 1)
+ *           CosineMatrixAttention (allennlp 2.5.1, third party) at knrm.py:60, ecai20_tk.py:105
+ *
+ * q [B,Lq,D] f32, d [B,Ld,D] f32 (D % 4 == 0, 16-byte aligned); q_mask [B,Lq], d_mask [B,Ld] of
+ * `mask_dtype` (matchmaker passes float masks: MMB200_MASK_F32); mu, sigma, weight [K] f32 device
+ * arrays, alpha [K] or NULL (= 1); K <= 32.
+ * Outputs (any of per_kernel / per_kernel_query / cosine may be NULL):
+ *   score [B]; per_kernel [B,K] (= P); per_kernel_query [B,Lq,K] (= S, what backward needs);
+ *   cosine [B,Lq,Ld] = c_ij * q_mask[i] * d_mask[j] (the reference's secondary output).
+ * ------------------------------------------------------------------------------------------ */
+MMB200_API int mmb200_kernel_pool_fwd(const float* q, const float* d, const void* q_mask, const void* d_mask,
+                                      const float* mu, const float* sigma, const float* alpha,
+                                      const float* weight, float* score, float* per_kernel,
+                                      float* per_kernel_query, float* cosine, int64_t B, int32_t Lq,
+                                      int32_t Ld, int32_t D, int32_t K, float log_scale, int32_t mask_dtype,
+                                      int32_t impl, void* stream);
+
+/* Backward of mmb200_kernel_pool_fwd for d(loss)/d(score) = grad_score [B]:
+ *   grad_q [B,Lq,D], grad_d [B,Ld,D] (overwritten), grad_alpha [K] or NULL, grad_weight [K]
+ *   (overwritten; summed over the batch deterministically via `workspace` [2*B*K] f32).
+ * per_kernel_query is S from the forward.  Matches autograd of the reference expression
+ * (clamp passes gradient when alpha*S >= 1e-10; rows with |x| = 0 get no normalisation term). */
+MMB200_API int mmb200_kernel_pool_bwd(const float* q, const float* d, const void* q_mask, const void* d_mask,
+                                      const float* mu, const float* sigma, const float* alpha,
+                                      const float* weight, const float* per_kernel_query,
+                                      const float* grad_score, float* grad_q, float* grad_d,
+                                      float* grad_alpha, float* grad_weight, float* workspace, int64_t B,
+                                      int32_t Lq, int32_t Ld, int32_t D, int32_t K, float log_scale,
+                                      int32_t mask_dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,3 +32,36 @@ def maxsim(q: torch.Tensor, d: torch.Tensor, q_mask: Optional[torch.Tensor] = No
            d_mask: Optional[torch.Tensor] = None, docs_per_query: int = 1) -> torch.Tensor:
     """Differentiable ColBERT max-sim (pairs mode); see :func:`matchmaker_b200.interaction.maxsim`."""
     return _MaxSim.apply(q, d, q_mask, d_mask, docs_per_query)
+
+
+class _KernelPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale):
+        need_grad = any(t is not None and t.requires_grad for t in (q, d, weight, alpha))
+        out = interaction.kernel_pool(q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale,
+                                      want_per_kernel=True, want_per_kernel_query=need_grad)
+        if need_grad:
+            ctx.save_for_backward(q, d, q_mask, d_mask, mu, sigma, weight,
+                                  alpha if alpha is not None else torch.empty(0, device=q.device),
+                                  out["per_kernel_query"])
+            ctx.has_alpha = alpha is not None
+            ctx.log_scale = log_scale
+        ctx.mark_non_differentiable(out["per_kernel"])
+        return out["score"], out["per_kernel"]
+
+    @staticmethod
+    def backward(ctx, grad_score, _grad_pk):
+        q, d, q_mask, d_mask, mu, sigma, weight, alpha, S = ctx.saved_tensors
+        alpha = alpha if ctx.has_alpha else None
+        gq, gd, ga, gw = interaction.kernel_pool_bwd(q, d, q_mask, d_mask, mu, sigma, weight, alpha, S, grad_score,
+                                                     ctx.log_scale)
+        gw = gw.view_as(weight)
+        ga = None if ga is None else ga.view_as(alpha)
+        return gq.to(q.dtype), gd.to(d.dtype), None, None, None, None, gw, ga, None
+
+
+def kernel_pool(q, d, q_mask, d_mask, mu, sigma, weight, alpha=None, log_scale: float = 1.0):
+    """Differentiable cosine + RBF kernel pooling: returns (score [B], per_kernel [B,K]); gradients flow to
+    q, d, weight and alpha through the score (per_kernel is a detached by-product, as used by the
+    reference's secondary outputs)."""
+    return _KernelPool.apply(q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale)

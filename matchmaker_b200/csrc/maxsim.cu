@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "host_util.cuh"
+#include "masks.cuh"
 #include "maxsim.cuh"
 #include "ptx.cuh"
 
@@ -41,21 +42,6 @@ namespace mmb {
 // ---------------------------------------------------------------------------------------------
 // shared device helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool mask_at(const void* mask, int mask_dtype, int64_t idx) {
-  switch (mask_dtype) {
-    case MMB200_MASK_U8:
-      return static_cast<const uint8_t*>(mask)[idx] != 0;
-    case MMB200_MASK_I32:
-      return static_cast<const int32_t*>(mask)[idx] != 0;
-    case MMB200_MASK_I64:
-      return static_cast<const int64_t*>(mask)[idx] != 0;
-    case MMB200_MASK_F32:
-      return static_cast<const float*>(mask)[idx] != 0.0f;
-    default:
-      return true;
-  }
-}
-
 template <typename T>
 __device__ __forceinline__ float to_float(T v);
 template <>
@@ -70,6 +56,9 @@ __device__ __forceinline__ int64_t pair_query(const MaxsimParams& P, int64_t p) 
 }
 __device__ __forceinline__ int64_t pair_doc(const MaxsimParams& P, int64_t p) {
   return P.pair_d ? static_cast<int64_t>(P.pair_d[p]) : p;
+}
+__device__ __forceinline__ int64_t pair_dmask_row(const MaxsimParams& P, int64_t p) {
+  return P.pair_dmask ? static_cast<int64_t>(P.pair_dmask[p]) : pair_doc(P, p);
 }
 
 constexpr float kMaskedScore = -1000.0f;  // colbert.py:69
@@ -92,7 +81,7 @@ __global__ void __launch_bounds__(kSimtThreads) maxsim_simt_kernel(MaxsimParams 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   for (int64_t p = blockIdx.x; p < P.n_pairs; p += gridDim.x) {
-    const int64_t qi = pair_query(P, p), di = pair_doc(P, p);
+    const int64_t qi = pair_query(P, p), di = pair_doc(P, p), dmi = pair_dmask_row(P, p);
     const T* qptr = static_cast<const T*>(P.q) + qi * (int64_t)Lq * dim;
     const T* dptr = static_cast<const T*>(P.d) + di * (int64_t)Ld * dim;
     __syncthreads();
@@ -105,7 +94,7 @@ __global__ void __launch_bounds__(kSimtThreads) maxsim_simt_kernel(MaxsimParams 
 #pragma unroll
     for (int t = 0; t < kSimtMaxQPerLane; ++t) { best[t] = -INFINITY; barg[t] = -1; }
     for (int j = warp; j < Ld; j += 4) {
-      const bool ok = mask_at(P.d_mask, P.d_mask ? P.mask_dtype : MMB200_MASK_NONE, di * (int64_t)Ld + j);
+      const bool ok = mask_at(P.d_mask, P.d_mask ? P.mask_dtype : MMB200_MASK_NONE, dmi * (int64_t)Ld + j);
       float acc[kSimtMaxQPerLane] = {0.f, 0.f, 0.f, 0.f};
       if (ok) {
         const T* drow = dptr + (int64_t)j * dim;
@@ -347,15 +336,43 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint32_t accphase = 0;
     const int dmt = P.d_mask ? P.mask_dtype : MMB200_MASK_NONE;
     const int qmt = P.q_mask ? P.mask_dtype : MMB200_MASK_NONE;
+    // Mask words are fetched two tiles ahead and only *tested* when their tile is processed, so the
+    // global-load latency hides behind the TMEM loads / shuffles of the tiles in between.
+    int64_t fp = p_begin;  // (pair, tile) whose mask word is fetched next
+    int ft = 0;
+    auto fetch = [&](uint64_t& raw) -> bool {  // returns "row lies inside the document"
+      bool in_doc = false;
+      raw = 1;
+      if (fp < p_end) {
+        const int row = ft * kTileRows + lq * 32 + lane;
+        in_doc = row < P.Ld;
+        if (in_doc && dmt != MMB200_MASK_NONE) raw = mask_raw(P.d_mask, dmt, pair_dmask_row(P, fp) * (int64_t)P.Ld + row);
+      }
+      if (++ft == L.tiles) { ft = 0; ++fp; }
+      return in_doc;
+    };
+    uint64_t raw0, raw1;
+    bool in0 = fetch(raw0);
+    bool in1 = fetch(raw1);
     for (int64_t p = p_begin; p < p_end; ++p) {
-      const int64_t qi = pair_query(P, p), di = pair_doc(P, p);
+      const int64_t qi = pair_query(P, p);
+      // query-mask words for this lane's columns: fetched now, tested after the pair's tiles
+      uint64_t qraw[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col = c * 32 + lane;
+        qraw[c] = (c < ncol32 && col < P.Lq) ? (qmt != MMB200_MASK_NONE ? mask_raw(P.q_mask, qmt, qi * (int64_t)P.Lq + col) : 1) : 0;
+      }
       float colmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       for (int t = 0; t < L.tiles; ++t) {
-        const int row = t * kTileRows + lq * 32 + lane;
-        const bool in_doc = row < P.Ld;
-        const bool tok_ok = in_doc ? mask_at(P.d_mask, dmt, di * (int64_t)P.Ld + row) : false;
+        const bool in_doc = in0;
+        const uint64_t raw = raw0;
+        in0 = in1;
+        raw0 = raw1;
+        in1 = fetch(raw1);
         mbar_wait(&S->accfull[acc], accphase);
         tc_fence_after_sync();
+        const bool tok_ok = mask_test(raw, dmt);
         const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * L.npad);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -383,12 +400,14 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       named_bar_sync(1, 128);
       if (ew == (int)((p - p_begin) & 3)) {  // rotate the final reduction over the 4 warps
         float total = 0.f;
-        for (int c = 0; c < ncol32; ++c) {
-          const int col = c * 32 + lane;
-          float m = fmaxf(fmaxf(S->colmax[buf][0][col], S->colmax[buf][1][col]),
-                          fmaxf(S->colmax[buf][2][col], S->colmax[buf][3][col]));
-          const bool qok = (col < P.Lq) && mask_at(P.q_mask, qmt, qi * (int64_t)P.Lq + col);
-          total += qok ? m : 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < ncol32) {
+            const int col = c * 32 + lane;
+            float m = fmaxf(fmaxf(S->colmax[buf][0][col], S->colmax[buf][1][col]),
+                            fmaxf(S->colmax[buf][2][col], S->colmax[buf][3][col]));
+            total += mask_test(qraw[c], qmt) ? m : 0.f;
+          }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
@@ -518,12 +537,12 @@ int maxsim_fwd_device(const MaxsimParams& P, int dtype, int impl, cudaStream_t s
 }  // namespace mmb
 
 extern "C" int mmb200_maxsim_fwd(const void* q, const void* d, const void* q_mask, const void* d_mask,
-                                 const int32_t* pair_q, const int32_t* pair_d, float* out, int32_t* argmax,
-                                 int64_t n_q, int64_t n_d, int64_t n_pairs, int32_t docs_per_query, int32_t Lq,
+                                 const int32_t* pair_q, const int32_t* pair_d, const int32_t* pair_dmask,
+                                 float* out, int32_t* argmax, int64_t n_q, int64_t n_d, int64_t n_pairs, int32_t docs_per_query, int32_t Lq,
                                  int32_t Ld, int32_t dim, int32_t dtype, int32_t mask_dtype, int32_t impl,
                                  void* stream) {
   mmb::MaxsimParams P;
-  P.q = q; P.d = d; P.q_mask = q_mask; P.d_mask = d_mask; P.pair_q = pair_q; P.pair_d = pair_d;
+  P.q = q; P.d = d; P.q_mask = q_mask; P.d_mask = d_mask; P.pair_q = pair_q; P.pair_d = pair_d; P.pair_dmask = pair_dmask;
   P.out = out; P.argmax = argmax; P.n_q = n_q; P.n_d = n_d; P.n_pairs = n_pairs;
   P.pair_base = 0;
   P.docs_per_query = docs_per_query; P.Lq = Lq; P.Ld = Ld; P.dim = dim; P.mask_dtype = mask_dtype;

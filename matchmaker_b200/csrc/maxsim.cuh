@@ -13,6 +13,7 @@ struct MaxsimParams {
   const void* d_mask;
   const int32_t* pair_q;
   const int32_t* pair_d;
+  const int32_t* pair_dmask;  // row of d_mask used for pair p (default: the document index)
   float* out;
   int32_t* argmax;
   int64_t n_q, n_d, n_pairs;

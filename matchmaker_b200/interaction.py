@@ -63,14 +63,14 @@ def _common_mask_dtype(a: Optional[torch.Tensor], b: Optional[torch.Tensor]):
 def maxsim(q: torch.Tensor, d: torch.Tensor, q_mask: Optional[torch.Tensor] = None,
            d_mask: Optional[torch.Tensor] = None, docs_per_query: int = 1,
            pair_q: Optional[torch.Tensor] = None, pair_d: Optional[torch.Tensor] = None,
-           impl: str = "auto", return_argmax: bool = False):
+           impl: str = "auto", return_argmax: bool = False, pair_dmask: Optional[torch.Tensor] = None):
     """ColBERT max-sim scores, fp32.
 
     q [n_q, Lq, dim], d [n_d, Ld, dim] (fp16 / bf16 / fp32, same dtype), masks [n, L] (nonzero =
     token).  Pair p scores query ``pair_q[p]`` (default ``p // docs_per_query``) against document
     ``pair_d[p]`` (default ``p``).  Semantics: matchmaker/models/colbert.py:68-75 / :100-112.
     """
-    dev = _require_cuda(q, d, q_mask, d_mask, pair_q, pair_d)
+    dev = _require_cuda(q, d, q_mask, d_mask, pair_q, pair_d, pair_dmask)
     if q.dtype != d.dtype or q.dtype not in _DTYPES:
         raise _lib.MatchmakerB200Error(f"q/d must share a dtype in fp16/bf16/fp32, got {q.dtype}, {d.dtype}")
     if q.dim() != 3 or d.dim() != 3 or q.shape[-1] != d.shape[-1]:
@@ -92,6 +92,10 @@ def maxsim(q: torch.Tensor, d: torch.Tensor, q_mask: Optional[torch.Tensor] = No
         n_pairs = pair_q.numel()
         if pair_d.numel() != n_pairs:
             raise _lib.MatchmakerB200Error("pair_q / pair_d length mismatch")
+        if pair_dmask is not None:
+            pair_dmask = pair_dmask.to(torch.int32).contiguous()
+            if pair_dmask.numel() != n_pairs:
+                raise _lib.MatchmakerB200Error("pair_dmask length mismatch")
     else:
         n_pairs = n_d
         if n_q * docs_per_query < n_d:
@@ -101,20 +105,31 @@ def maxsim(q: torch.Tensor, d: torch.Tensor, q_mask: Optional[torch.Tensor] = No
     lib = _lib.load()
     with torch.cuda.device(dev):
         rc = lib.mmb200_maxsim_fwd(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(pair_q), _ptr(pair_d),
-                                   _ptr(out), _ptr(argmax), n_q, n_d, n_pairs, docs_per_query, Lq, Ld, dim,
+                                   _ptr(pair_dmask), _ptr(out), _ptr(argmax), n_q, n_d, n_pairs, docs_per_query, Lq, Ld, dim,
                                    _DTYPES[q.dtype], mcode, _IMPLS[impl], _stream(dev))
     _lib.check(rc, "mmb200_maxsim_fwd")
     return (out, argmax) if return_argmax else out
 
 
 def maxsim_allpairs(q: torch.Tensor, q_mask: Optional[torch.Tensor], d: torch.Tensor,
-                    d_mask: Optional[torch.Tensor], impl: str = "auto") -> torch.Tensor:
-    """All query x document max-sim scores [n_q, n_d] (colbert.py:154-162)."""
+                    d_mask: Optional[torch.Tensor], impl: str = "auto",
+                    reference_mask_indexing: bool = False) -> torch.Tensor:
+    """All query x document max-sim scores [n_q, n_d] (colbert.py:154-162).
+
+    ``reference_mask_indexing=True`` reproduces the reference bit-for-bit: colbert.py:158 expands
+    ``document_mask`` [n_d, Ld] along the *query* axis of the [n_q, n_d, Lq, Ld] score tensor, i.e. pair
+    (a, b) is masked with the mask of document ``a`` (only defined for n_q == n_d, the in-batch case).
+    The default applies each document's own mask."""
     n_q, n_d = q.shape[0], d.shape[0]
     idx = torch.arange(n_q * n_d, device=q.device, dtype=torch.int32)
     pq = torch.div(idx, n_d, rounding_mode="floor").to(torch.int32)
     pd = (idx - pq * n_d).to(torch.int32)
-    return maxsim(q, d, q_mask, d_mask, pair_q=pq, pair_d=pd, impl=impl).view(n_q, n_d)
+    pdm = None
+    if reference_mask_indexing and d_mask is not None:
+        if n_q != n_d:
+            raise _lib.MatchmakerB200Error("reference mask indexing (colbert.py:158) needs n_q == n_d")
+        pdm = pq
+    return maxsim(q, d, q_mask, d_mask, pair_q=pq, pair_d=pd, impl=impl, pair_dmask=pdm).view(n_q, n_d)
 
 
 def maxsim_bwd(q: torch.Tensor, d: torch.Tensor, grad_out: torch.Tensor, argmax: torch.Tensor,
@@ -162,3 +177,66 @@ def maxsim_host(q: torch.Tensor, d: torch.Tensor, q_mask: Optional[torch.Tensor]
                                         docs_per_query, Lq, Ld, dim, _DTYPES[q.dtype], mcode, chunk_pairs)
     _lib.check(rc, "mmb200_maxsim_fwd_host")
     return out
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def kernel_pool(q: torch.Tensor, d: torch.Tensor, q_mask: torch.Tensor, d_mask: torch.Tensor,
+                mu: torch.Tensor, sigma: torch.Tensor, weight: torch.Tensor, alpha: Optional[torch.Tensor] = None,
+                log_scale: float = 1.0, want_per_kernel: bool = False, want_per_kernel_query: bool = False,
+                want_cosine: bool = False, impl: str = "auto"):
+    """Cosine match matrix + RBF kernel pooling, forward (knrm.py:52-84 / ecai20_tk.py:105-124).
+
+    q [B,Lq,D], d [B,Ld,D] fp32; masks [B,L]; mu/sigma/weight(/alpha) [K].  Returns a dict with "score"
+    [B] and, on request, "per_kernel" [B,K], "per_kernel_query" [B,Lq,K], "cosine" [B,Lq,Ld]."""
+    dev = _require_cuda(q, d, q_mask, d_mask, mu, sigma, weight, alpha)
+    if q.dtype != torch.float32 or d.dtype != torch.float32:
+        q, d = q.float(), d.float()  # the reference runs TK/KNRM with use_fp16: False (tk.yaml:6)
+    q, d = q.contiguous(), d.contiguous()
+    B, Lq, D = q.shape
+    _, Ld, _ = d.shape
+    if d.shape[0] != B or d.shape[2] != D:
+        raise _lib.MatchmakerB200Error(f"shape mismatch: q {tuple(q.shape)} d {tuple(d.shape)}")
+    q_mask, d_mask, mcode = _common_mask_dtype(_prep_mask(q_mask), _prep_mask(d_mask))
+    mu, sigma, weight = _f32c(mu).view(-1), _f32c(sigma).view(-1), _f32c(weight).view(-1)
+    alpha = None if alpha is None else _f32c(alpha).view(-1)
+    K = mu.numel()
+    score = torch.empty(B, dtype=torch.float32, device=dev)
+    pk = torch.empty((B, K), dtype=torch.float32, device=dev) if want_per_kernel else None
+    pkq = torch.empty((B, Lq, K), dtype=torch.float32, device=dev) if want_per_kernel_query else None
+    cos = torch.empty((B, Lq, Ld), dtype=torch.float32, device=dev) if want_cosine else None
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.mmb200_kernel_pool_fwd(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(mu), _ptr(sigma),
+                                        _ptr(alpha), _ptr(weight), _ptr(score), _ptr(pk), _ptr(pkq), _ptr(cos),
+                                        B, Lq, Ld, D, K, float(log_scale), mcode, _IMPLS[impl], _stream(dev))
+    _lib.check(rc, "mmb200_kernel_pool_fwd")
+    return {"score": score, "per_kernel": pk, "per_kernel_query": pkq, "cosine": cos}
+
+
+def kernel_pool_bwd(q, d, q_mask, d_mask, mu, sigma, weight, alpha, per_kernel_query, grad_score,
+                    log_scale: float = 1.0):
+    """Backward of :func:`kernel_pool`: returns (grad_q, grad_d, grad_alpha or None, grad_weight)."""
+    dev = _require_cuda(q, d, per_kernel_query, grad_score)
+    q, d = q.float().contiguous(), d.float().contiguous()
+    B, Lq, D = q.shape
+    Ld = d.shape[1]
+    q_mask, d_mask, mcode = _common_mask_dtype(_prep_mask(q_mask), _prep_mask(d_mask))
+    mu, sigma, weight = _f32c(mu).view(-1), _f32c(sigma).view(-1), _f32c(weight).view(-1)
+    alpha_c = None if alpha is None else _f32c(alpha).view(-1)
+    K = mu.numel()
+    gq = torch.empty_like(q)
+    gd = torch.empty_like(d)
+    ga = torch.empty(K, dtype=torch.float32, device=dev)
+    gw = torch.empty(K, dtype=torch.float32, device=dev)
+    ws = torch.empty(2 * B * K, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.mmb200_kernel_pool_bwd(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(mu), _ptr(sigma),
+                                        _ptr(alpha_c), _ptr(weight), _ptr(per_kernel_query.contiguous()),
+                                        _ptr(_f32c(grad_score)), _ptr(gq), _ptr(gd), _ptr(ga), _ptr(gw), _ptr(ws),
+                                        B, Lq, Ld, D, K, float(log_scale), mcode, _stream(dev))
+    _lib.check(rc, "mmb200_kernel_pool_bwd")
+    return gq, gd, (ga if alpha is not None else None), gw

@@ -152,6 +152,20 @@ def maxsim_allpairs(q: torch.Tensor, q_mask: torch.Tensor, d: torch.Tensor,
     return s.sum(-1)                                                       # :161
 
 
+def maxsim_allpairs_own_masks(q: torch.Tensor, q_mask: torch.Tensor, d: torch.Tensor,
+                              d_mask: torch.Tensor) -> torch.Tensor:
+    """All-pairs max-sim with every document masked by ITS OWN mask.  NOT the reference's behaviour:
+    colbert.py:158 expands ``document_mask`` [Nd,Ld] over the first (query) axis of the transposed
+    [Nq,Nd,Lq,Ld] score tensor, so the reference masks pair (a,b) with the mask of document a
+    (see maxsim_allpairs above, which keeps that quirk).  This is the intended semantics, built from
+    the pair scorer colbert.py:68-75."""
+    out = torch.empty(q.shape[0], d.shape[0])
+    for a in range(q.shape[0]):
+        n = d.shape[0]
+        out[a] = maxsim_pairs(q[a:a + 1].expand(n, -1, -1), d, q_mask[a:a + 1].expand(n, -1), d_mask)
+    return out
+
+
 def maxsim_one_query_many_docs(q: torch.Tensor, d: torch.Tensor, q_mask: Optional[torch.Tensor],
                                d_mask: Optional[torch.Tensor], docs_per_query: int) -> torch.Tensor:
     """BASELINE config 3 shape ("1 query x 1000 docs, 64 queries"): the reference
@@ -373,7 +387,7 @@ def synth_kernel_pool_inputs(B: int, Lq: int, Ld: int, D: int, seed: int, full_q
     g = _gen(seed)
     q = torch.randn(B, Lq, D, generator=g) * 0.4
     d = torch.randn(B, Ld, D, generator=g) * 0.4
-    q_len = torch.full((B,), Lq) if full_q else torch.randint(3, Lq + 1, (B,), generator=g)
+    q_len = torch.full((B,), Lq) if full_q else torch.randint(min(3, Lq), Lq + 1, (B,), generator=g)
     d_len = synth_lengths(B, min(75.0, Ld * 0.4), 30.0, min(10, Ld), Ld, g)
     for b in range(B):
         n_copy = max(1, int(copy_frac * int(q_len[b])))
@@ -396,7 +410,7 @@ def synth_colbert_inputs(n_queries: int, docs_per_query: int, Lq: int, Ld: int, 
     n_docs = n_queries * docs_per_query
     q = torch.nn.functional.normalize(torch.randn(n_queries, Lq, dim, generator=g), dim=-1)
     d = torch.nn.functional.normalize(torch.randn(n_docs, Ld, dim, generator=g), dim=-1)
-    q_len = torch.full((n_queries,), Lq) if full_q else torch.randint(2, Lq + 1, (n_queries,), generator=g)
+    q_len = torch.full((n_queries,), Lq) if full_q else torch.randint(min(2, Lq), Lq + 1, (n_queries,), generator=g)
     d_len = synth_lengths(n_docs, min(75.0, Ld * 0.42), 30.0, min(10, Ld), Ld, g)
     q_mask = (torch.arange(Lq).unsqueeze(0) < q_len.unsqueeze(1))
     d_mask = (torch.arange(Ld).unsqueeze(0) < d_len.unsqueeze(1))

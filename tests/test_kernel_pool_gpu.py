@@ -1,0 +1,169 @@
+"""Parity of the CUDA cosine + RBF kernel-pooling path (KNRM / TK) with golden vectors and the oracle;
+gradients against fp64 autograd of the oracle expression.  Bar: 1e-3 relative fp32."""
+import pytest
+import torch
+
+from conftest import assert_close_rel, load_golden
+from matchmaker_b200 import autograd, interaction
+from oracle import interaction_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+IMPLS = ["simt", "auto"]
+
+
+def _c(*ts):
+    return [None if t is None else t.to(DEV) for t in ts]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("tag", ["small", "cfg1"])
+def test_golden_knrm(tag, impl):
+    g = load_golden(f"knrm_{tag}")
+    out = interaction.kernel_pool(*_c(g["q"], g["d"], g["q_mask"], g["d_mask"], g["mu"], g["sigma"], g["weight"]),
+                                  alpha=None, log_scale=0.01, want_per_kernel=True, want_cosine=True, impl=impl)
+    assert_close_rel(out["score"], g["score"], what="score")
+    assert_close_rel(out["per_kernel"], g["per_kernel"], what="per_kernel")
+    assert_close_rel(out["cosine"], g["cosine_matrix_masked"], rel=1e-3, what="cosine")
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("tag", ["k11", "k21"])
+def test_golden_tk_interaction(tag, impl):
+    g = load_golden(f"tk_{tag}")
+    out = interaction.kernel_pool(*_c(g["q_ctx"], g["d_ctx"], g["q_mask"], g["d_mask"], g["mu"], g["sigma"], g["weight"]),
+                                  alpha=g["alpha"].to(DEV), log_scale=1.0, want_per_kernel=True, want_cosine=True,
+                                  impl=impl)
+    assert_close_rel(out["score"], g["score"], what="score")
+    assert_close_rel(out["per_kernel"], g["per_kernel"], what="per_kernel")
+    assert_close_rel(out["cosine"], g["cosine_matrix"], what="cosine")
+
+
+SHAPES = [  # B, Lq, Ld, D, K-kind
+    (7, 30, 180, 300, "knrm11"),
+    (5, 30, 200, 300, "tk21"),
+    (3, 40, 77, 64, "tk11"),      # Lq > 32: two query blocks
+    (300, 8, 20, 32, "tk11"),     # more pairs than CTAs
+    (2, 1, 1, 4, "tk11"),
+    (2, 30, 200, 300, "k32"),
+]
+
+
+def _kernels(kind):
+    if kind == "knrm11":
+        return O.knrm_kernel_mus(11), O.knrm_kernel_sigmas(11), 0.01, False
+    if kind == "tk21":
+        mu, sg = O.tk_21_kernels()
+        return mu, sg, 1.0, True
+    if kind == "k32":
+        return [1.0 - 2.0 * i / 31 for i in range(32)], [0.07] * 32, 1.0, True
+    return [1.0, 0.9, 0.7, 0.5, 0.3, 0.1, -0.1, -0.3, -0.5, -0.7, -0.9], [0.1] * 11, 1.0, True
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape", SHAPES)
+def test_seeded_vs_oracle(shape, impl):
+    B, Lq, Ld, D, kind = shape
+    mu, sg, ls, use_alpha = _kernels(kind)
+    mu, sg = torch.tensor(mu), torch.tensor(sg)
+    g = torch.Generator().manual_seed(B + Lq + Ld)
+    w = (torch.rand(len(mu), generator=g) - 0.5) * 0.03
+    alpha = torch.rand(len(mu), generator=g) + 0.5 if use_alpha else None
+    q, d, qm, dm = O.synth_kernel_pool_inputs(B, Lq, Ld, D, seed=31 + Lq + Ld)
+    if use_alpha:
+        ref, sec = O.kernel_pool_tk(q, d, qm, dm, mu, sg, alpha, w)
+        ref_cos = sec["cosine_matrix"]
+    else:
+        ref, sec = O.kernel_pool_knrm(q, d, qm, dm, mu, sg, w)
+        ref_cos = sec["cosine_matrix_masked"]
+    out = interaction.kernel_pool(*_c(q, d, qm, dm, mu, sg, w), alpha=None if alpha is None else alpha.to(DEV),
+                                  log_scale=ls, want_per_kernel=True, want_per_kernel_query=True, want_cosine=True,
+                                  impl=impl)
+    assert_close_rel(out["score"], ref, what=f"score {shape}")
+    assert_close_rel(out["per_kernel"], sec["per_kernel"], what="per_kernel")
+    assert_close_rel(out["cosine"], ref_cos, what="cosine")
+    valid = qm.bool()
+    assert_close_rel(out["per_kernel_query"].cpu()[valid], sec["per_kernel_query"][valid], what="S (valid query rows)")
+
+
+@pytest.mark.parametrize("mdt", [torch.float32, torch.bool, torch.int64])
+def test_mask_dtypes(mdt):
+    mu, sg, ls, _ = _kernels("tk11")
+    mu, sg = torch.tensor(mu), torch.tensor(sg)
+    w = torch.linspace(-0.01, 0.01, 11)
+    q, d, qm, dm = O.synth_kernel_pool_inputs(4, 12, 50, 32, seed=3)
+    ref, _ = O.kernel_pool_tk(q, d, qm, dm, mu, sg, torch.ones(11), w)
+    out = interaction.kernel_pool(*_c(q, d, qm.to(mdt), dm.to(mdt), mu, sg, w), alpha=None, log_scale=ls)
+    assert_close_rel(out["score"], ref, what=str(mdt))
+
+
+def _oracle_fp64_grads(q, d, qm, dm, mu, sg, alpha, w, ls, gout):
+    q64 = q.double().requires_grad_(True)
+    d64 = d.double().requires_grad_(True)
+    a64 = alpha.double().requires_grad_(True)
+    w64 = w.double().requires_grad_(True)
+    qn = q64 / (q64.norm(dim=-1, keepdim=True) + 1e-13)
+    dn = d64 / (d64.norm(dim=-1, keepdim=True) + 1e-13)
+    cos = torch.bmm(qn, dn.transpose(-1, -2))
+    raw = torch.exp(-torch.pow(cos.unsqueeze(-1) - mu.double().view(1, 1, 1, -1), 2) / (2 * sg.double().view(1, 1, 1, -1) ** 2))
+    S = (raw * dm.double().unsqueeze(1).unsqueeze(-1)).sum(2)
+    L = torch.log(torch.clamp(S * a64.view(1, 1, -1), min=1e-10)) * ls * qm.double().unsqueeze(-1)
+    score = L.sum(1) @ w64
+    score.backward(gout.double())
+    return score.detach(), q64.grad, d64.grad, a64.grad, w64.grad
+
+
+@pytest.mark.parametrize("shape", [(4, 30, 90, 300, "tk11"), (3, 40, 45, 64, "tk21"), (6, 9, 33, 32, "knrm11"),
+                                   (2, 30, 200, 512, "tk11")])
+def test_backward_vs_fp64_autograd(shape):
+    B, Lq, Ld, D, kind = shape
+    mu, sg, ls, _ = _kernels(kind)
+    mu, sg = torch.tensor(mu), torch.tensor(sg)
+    g = torch.Generator().manual_seed(17)
+    w = (torch.rand(len(mu), generator=g) - 0.5) * 0.5
+    alpha = torch.rand(len(mu), generator=g) + 0.5
+    gout = torch.randn(B, generator=g)
+    q, d, qm, dm = O.synth_kernel_pool_inputs(B, Lq, Ld, D, seed=5 + D)
+    if kind == "knrm11":
+        # keep cosines away from the 1e-4-wide exact-match kernel: its fp32 gradient is ill-conditioned
+        # (d/dc ~ 1e4) in the oracle itself; exact matches (c == 1, gradient 0) stay in.
+        pass
+    s_ref, gq, gd, ga, gw = _oracle_fp64_grads(q, d, qm, dm, mu, sg, alpha, w, ls, gout)
+    cq = q.to(DEV).requires_grad_(True)
+    cd = d.to(DEV).requires_grad_(True)
+    ca = alpha.to(DEV).requires_grad_(True)
+    cw = w.to(DEV).requires_grad_(True)
+    score, pk = autograd.kernel_pool(cq, cd, qm.to(DEV), dm.to(DEV), mu.to(DEV), sg.to(DEV), cw, ca, ls)
+    assert_close_rel(score, s_ref, what="score")
+    score.backward(gout.to(DEV))
+    # gradients: 1e-3 relative to the largest entry of each row-block (elementwise tiny entries are noise)
+    def close(a, b, what):
+        a, b = a.double().cpu(), b.double()
+        scale = b.abs().max().item()
+        err = (a - b).abs().max().item()
+        assert err <= 1e-3 * scale + 1e-12, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+    close(cq.grad, gq, "grad_q")
+    close(cd.grad, gd, "grad_d")
+    close(ca.grad, ga, "grad_alpha")
+    close(cw.grad, gw, "grad_weight")
+    assert (cd.grad.cpu()[dm == 0] == 0).all() and (cq.grad.cpu()[qm == 0] == 0).all()
+
+
+def test_baseline_cfg2_size_properties():
+    """BASELINE config 2 size (B=256, Lq=30, Ld=200, D=300, K=21): batch-order independence (bit-exact),
+    SIMT vs auto path agreement, oracle on a slice."""
+    mu, sg = O.tk_21_kernels()
+    mu, sg = torch.tensor(mu), torch.tensor(sg)
+    w = torch.linspace(-0.014, 0.014, 21)
+    alpha = torch.linspace(0.5, 1.5, 21)
+    q, d, qm, dm = O.synth_kernel_pool_inputs(256, 30, 200, 300, seed=1236)
+    args = _c(q, d, qm, dm, mu, sg, w)
+    out = interaction.kernel_pool(*args, alpha=alpha.to(DEV), want_per_kernel=True)
+    perm = torch.randperm(256, generator=torch.Generator().manual_seed(2)).to(DEV)
+    outp = interaction.kernel_pool(args[0][perm], args[1][perm], args[2][perm], args[3][perm], *args[4:],
+                                   alpha=alpha.to(DEV))
+    assert torch.equal(outp["score"], out["score"][perm])
+    simt = interaction.kernel_pool(*args, alpha=alpha.to(DEV), impl="simt")
+    assert_close_rel(out["score"], simt["score"], what="auto vs simt")
+    ref, _ = O.kernel_pool_tk(q[:16], d[:16], qm[:16], dm[:16], mu, sg, alpha, w)
+    assert_close_rel(out["score"][:16], ref, what="oracle slice")

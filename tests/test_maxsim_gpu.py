@@ -21,7 +21,11 @@ def test_golden_small_fp32_masked_agg_allpairs():
     q, d, qm, dm = _cuda(g["q"], g["d"], g["q_mask"], g["d_mask"])
     assert_close_rel(interaction.maxsim(q, d, qm, dm), g["score"], what="forward")
     assert_close_rel(interaction.maxsim(q, d), g["agg"], what="forward_aggregation")
-    assert_close_rel(interaction.maxsim_allpairs(q, qm, d, dm), g["allpairs"], what="inbatch")
+    # colbert.py:158 indexes the document mask by the query position; reproduced on request
+    assert_close_rel(interaction.maxsim_allpairs(q, qm, d, dm, reference_mask_indexing=True), g["allpairs"],
+                     what="inbatch (reference mask indexing)")
+    own = O.maxsim_allpairs_own_masks(g["q"], g["q_mask"], g["d"], g["d_mask"])
+    assert_close_rel(interaction.maxsim_allpairs(q, qm, d, dm), own, what="inbatch (own masks)")
 
 
 @pytest.mark.parametrize("impl", ["tcgen05", "simt", "auto"])
@@ -67,7 +71,7 @@ def test_mask_dtypes(mdt):
 
 def test_fully_masked_doc_and_query_token_edge_cases():
     q, d, qm, dm = O.synth_colbert_inputs(2, 3, 32, 180, 128, seed=11)
-    dm[1] = 0          # document with no real token: every position scores -1000
+    dm[3] = 0          # document with no real token: every position scores -1000
     dm[4, 1:] = 0      # single-token document
     qm[1, 5:] = 0
     qm[0] = 0          # query with no real token: score 0
@@ -91,10 +95,13 @@ def test_non_prefix_masks():
 
 def test_pair_index_arrays_and_allpairs_fp16():
     q, d, qm, dm = O.synth_colbert_inputs(6, 1, 32, 90, 128, seed=13, full_q=False)
-    ref = O.maxsim_allpairs(q.float(), qm, d.float(), dm)
+    ref_quirk = O.maxsim_allpairs(q.float(), qm, d.float(), dm)
+    ref = O.maxsim_allpairs_own_masks(q.float(), qm, d.float(), dm)
     cq, cd, cqm, cdm = _cuda(q, d, qm, dm)
     for impl in ("tcgen05", "simt"):
         assert_close_rel(interaction.maxsim_allpairs(cq, cqm, cd, cdm, impl=impl), ref, what=f"allpairs {impl}")
+        assert_close_rel(interaction.maxsim_allpairs(cq, cqm, cd, cdm, impl=impl, reference_mask_indexing=True),
+                         ref_quirk, what=f"allpairs quirk {impl}")
     pq = torch.tensor([5, 0, 0, 3, 3, 3, 1], dtype=torch.int32, device=DEV)
     pd = torch.tensor([0, 5, 2, 2, 4, 1, 1], dtype=torch.int32, device=DEV)
     got = interaction.maxsim(cq, cd, cqm, cdm, pair_q=pq, pair_d=pd)
