@@ -270,7 +270,7 @@ def main():
                     "note": "mmb200_maxsim_fwd_host: pinned host q/d/masks -> chunked H2D overlapped with the "
                             "kernel -> D2H scores; PCIe-bound"},
             "gpu_launches": args.steps,
-            "roofline": {"bound": "hbm", "kernel": "maxsim_tc_kernel<2>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "maxsim_qm_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "algorithmic_bytes_per_pair": ALG_BYTES_PER_PAIR},

@@ -58,6 +58,7 @@ extern "C" {
 #define MMB200_IMPL_AUTO 0
 #define MMB200_IMPL_SIMT 1    /* CUDA-core kernel, any shape/dtype */
 #define MMB200_IMPL_TCGEN05 2 /* TMA + tcgen05 tensor-core kernel (fails if shape unsupported) */
+#define MMB200_IMPL_TCGEN05_DOCM 3 /* max-sim only: the first-generation "documents on M" tcgen05 kernel */
 
 MMB200_API int mmb200_version(void);
 MMB200_API const char* mmb200_last_error(void);

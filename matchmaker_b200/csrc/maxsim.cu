@@ -524,9 +524,14 @@ int maxsim_fwd_device(const MaxsimParams& P, int dtype, int impl, cudaStream_t s
               std::to_string(dev.cc_minor));
     return MMB200_ERR_UNSUPPORTED;
   }
+  if (impl == MMB200_IMPL_AUTO || impl == MMB200_IMPL_TCGEN05) {
+    bool handled = false;
+    const int rc = maxsim_qm_launch(P, dtype, dev, stream, &handled);
+    if (handled || rc != MMB200_OK) return rc;
+  }
   std::string why;
   const bool tc_ok = tc_supported(P, dtype, &why);
-  if (impl == MMB200_IMPL_TCGEN05 && !tc_ok) {
+  if ((impl == MMB200_IMPL_TCGEN05 || impl == MMB200_IMPL_TCGEN05_DOCM) && !tc_ok) {
     set_error(why);
     return MMB200_ERR_UNSUPPORTED;
   }

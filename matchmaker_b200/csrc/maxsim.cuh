@@ -21,6 +21,10 @@ struct MaxsimParams {
   int32_t docs_per_query, Lq, Ld, dim, mask_dtype;
 };
 
+struct DeviceInfo;
+// maxsim_qm.cu: "queries on M" tcgen05 kernel (Lq <= 32, dim 64/128); *handled = false if out of envelope.
+int maxsim_qm_launch(const MaxsimParams& P, int dtype, const DeviceInfo& dev, cudaStream_t stream, bool* handled);
+
 // Validates, picks SIMT or tcgen05 and launches on `stream`.
 int maxsim_fwd_device(const MaxsimParams& P, int dtype, int impl, cudaStream_t stream);
 

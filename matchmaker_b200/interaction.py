@@ -14,7 +14,8 @@ from . import _lib
 _DTYPES = {torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float32: _lib.F32}
 _MASK_DTYPES = {torch.bool: _lib.MASK_U8, torch.uint8: _lib.MASK_U8, torch.int32: _lib.MASK_I32,
                 torch.int64: _lib.MASK_I64, torch.float32: _lib.MASK_F32}
-_IMPLS = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}
+_IMPLS = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05,
+          "tcgen05_docm": _lib.IMPL_TCGEN05_DOCM}
 
 
 def _require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:

@@ -21,6 +21,10 @@ STAGES = [
     (3, 500, 32, 180, 128, "f16", True),
     (4, 2, 64, 57, 256, "bf16", True),
     (2, 5, 128, 129, 192, "f16", True),
+    (3, 7, 17, 300, 64, "f16", True),
+    (2, 4, 32, 255, 128, "bf16", True),
+    (2, 4, 32, 256, 128, "f16", True),
+    (2, 3, 32, 700, 128, "f16", True),
 ]
 
 
@@ -36,7 +40,7 @@ def run_stage(i):
     ref = O.maxsim_one_query_many_docs(q.float(), d.float(), qm, dm, dpq)
     dev = "cuda"
     args = [t.to(dev) if t is not None else None for t in (q, d, qm, dm)]
-    for impl in ("simt", "tcgen05"):
+    for impl in ("simt", "tcgen05_docm", "tcgen05"):
         got = interaction.maxsim(*args, docs_per_query=dpq, impl=impl)
         torch.cuda.synchronize()
         err = (got.cpu() - ref).abs().max().item()
@@ -53,13 +57,13 @@ def timing():
     from oracle import interaction_oracle as O
     n_q, dpq = 64, 1000
     q, d, qm, dm = O.synth_colbert_inputs(n_q, dpq, 32, 180, 128, seed=1237)
-    args = [t.cuda() for t in (q, d, qm, dm)]
-    bytes_per_pair = 180 * 128 * 2 + 180 * 8 + 4
-    for impl in ("tcgen05", "simt"):
+    args = [t.cuda() for t in (q, d, qm.bool(), dm.bool())]
+    bytes_per_pair = 180 * 128 * 2 + 180 + 4
+    for impl in ("tcgen05", "tcgen05_docm", "simt"):
         for _ in range(3):
             interaction.maxsim(*args, docs_per_query=dpq, impl=impl)
         torch.cuda.synchronize()
-        n = 20 if impl == "tcgen05" else 3
+        n = 20 if impl != "simt" else 3
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):

@@ -6,6 +6,6 @@ timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpu
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:maxsim_tc -s 3 -c 2 -f -o gpurun_out/prof_maxsim \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:maxsim_qm -s 3 -c 2 -f -o gpurun_out/prof_maxsim \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1
 cat gpurun_out/pytest_gpu.log; cat gpurun_out/bench.json; cat gpurun_out/bench_ref.json; tail -3 gpurun_out/bench.err

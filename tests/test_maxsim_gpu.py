@@ -28,7 +28,7 @@ def test_golden_small_fp32_masked_agg_allpairs():
     assert_close_rel(interaction.maxsim_allpairs(q, qm, d, dm), own, what="inbatch (own masks)")
 
 
-@pytest.mark.parametrize("impl", ["tcgen05", "simt", "auto"])
+@pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_docm", "simt", "auto"])
 def test_golden_cfg3_shape_fp16(impl):
     g = load_golden("colbert_cfg3")
     q, d, qm, dm = _cuda(g["q"], g["d"], g["q_mask"], g["d_mask"])
@@ -43,11 +43,14 @@ SHAPES = [  # n_q, docs_per_query, Lq, Ld, dim, dtype
     (2, 5, 128, 129, 192, torch.float16),   # NPAD=128 (512 TMEM cols), odd k-block count
     (300, 1, 32, 180, 128, torch.float16),  # query changes every pair; more pairs than SMs
     (1, 1, 1, 1, 64, torch.float16),
+    (2, 4, 32, 255, 128, torch.bfloat16),   # Ld + 1 == 256: one 256-row tile in the queries-on-M kernel
+    (2, 4, 32, 256, 128, torch.float16),    # Ld + 1 == 257: two tiles
+    (2, 3, 30, 700, 64, torch.float16),     # long documents, three tiles
 ]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+@pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_docm", "simt"])
 def test_seeded_vs_oracle(shape, impl):
     n_q, dpq, Lq, Ld, dim, dt = shape
     q, d, qm, dm = O.synth_colbert_inputs(n_q, dpq, Lq, Ld, dim, seed=99 + Lq + Ld, dtype=dt, full_q=False)
@@ -77,7 +80,7 @@ def test_fully_masked_doc_and_query_token_edge_cases():
     qm[0] = 0          # query with no real token: score 0
     ref = O.maxsim_one_query_many_docs(q.float(), d.float(), qm, dm, 3)
     cq, cd, cqm, cdm = _cuda(q, d, qm, dm)
-    for impl in ("tcgen05", "simt"):
+    for impl in ("tcgen05", "tcgen05_docm", "simt"):
         assert_close_rel(interaction.maxsim(cq, cd, cqm, cdm, docs_per_query=3, impl=impl), ref, what=impl)
     assert ref[3].item() == -1000.0 * 5
 
@@ -89,7 +92,7 @@ def test_non_prefix_masks():
     qm = (torch.rand(qm.shape, generator=g) > 0.3).long()
     ref = O.maxsim_one_query_many_docs(q.float(), d.float(), qm, dm, 2)
     cq, cd, cqm, cdm = _cuda(q, d, qm, dm)
-    for impl in ("tcgen05", "simt"):
+    for impl in ("tcgen05", "tcgen05_docm", "simt"):
         assert_close_rel(interaction.maxsim(cq, cd, cqm, cdm, docs_per_query=2, impl=impl), ref, what=impl)
 
 
@@ -98,7 +101,7 @@ def test_pair_index_arrays_and_allpairs_fp16():
     ref_quirk = O.maxsim_allpairs(q.float(), qm, d.float(), dm)
     ref = O.maxsim_allpairs_own_masks(q.float(), qm, d.float(), dm)
     cq, cd, cqm, cdm = _cuda(q, d, qm, dm)
-    for impl in ("tcgen05", "simt"):
+    for impl in ("tcgen05", "tcgen05_docm", "simt"):
         assert_close_rel(interaction.maxsim_allpairs(cq, cqm, cd, cdm, impl=impl), ref, what=f"allpairs {impl}")
         assert_close_rel(interaction.maxsim_allpairs(cq, cqm, cd, cdm, impl=impl, reference_mask_indexing=True),
                          ref_quirk, what=f"allpairs quirk {impl}")
@@ -138,6 +141,8 @@ def test_baseline_size_properties():
     assert s.shape == (n_q * dpq,) and torch.isfinite(s).all()
     s_simt = interaction.maxsim(cq, cd, cqm, cdm, docs_per_query=dpq, impl="simt")
     assert_close_rel(s, s_simt, what="tc vs simt")
+    s_docm = interaction.maxsim(cq, cd, cqm, cdm, docs_per_query=dpq, impl="tcgen05_docm")
+    assert_close_rel(s, s_docm, what="queries-on-M vs documents-on-M kernel")
     # a document's score does not depend on where it sits in the batch
     perm = torch.randperm(n_q * dpq, generator=torch.Generator().manual_seed(5)).to(DEV)
     pq = torch.div(perm, dpq, rounding_mode="floor").to(torch.int32)
