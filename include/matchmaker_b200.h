@@ -154,6 +154,14 @@ MMB200_API int mmb200_kernel_pool_bwd(const float* q, const float* d, const void
                                       int32_t Lq, int32_t Ld, int32_t D, int32_t K, float log_scale,
                                       int32_t mask_dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * BERT_DOT pair scoring: out[b] = <q[b], d[b]>, fp32 accumulate.
+ * Replaces: BERT_Dot.forward   matchmaker/models/bert_dot.py:62  (bmm([B,1,dim],[B,dim,1]))
+ * q, d [B, dim] of `dtype`; out [B] f32.
+ * ------------------------------------------------------------------------------------------ */
+MMB200_API int mmb200_dot_pairs(const void* q, const void* d, float* out, int64_t B, int32_t dim,
+                                int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,3 +65,22 @@ def kernel_pool(q, d, q_mask, d_mask, mu, sigma, weight, alpha=None, log_scale: 
     q, d, weight and alpha through the score (per_kernel is a detached by-product, as used by the
     reference's secondary outputs)."""
     return _KernelPool.apply(q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale)
+
+
+class _DotPairs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qv, dv):
+        ctx.save_for_backward(qv, dv)
+        return interaction.dot_pairs(qv, dv)
+
+    @staticmethod
+    def backward(ctx, g):
+        qv, dv = ctx.saved_tensors
+        # d<q,d>/dq = g*d, d/dd = g*q: a broadcast multiply on [B,dim] (not an interaction kernel)
+        g = g.unsqueeze(-1)
+        return (g * dv.float()).to(qv.dtype), (g * qv.float()).to(dv.dtype)
+
+
+def dot_pairs(qv: torch.Tensor, dv: torch.Tensor) -> torch.Tensor:
+    """Differentiable BERT_DOT pair score (bert_dot.py:62)."""
+    return _DotPairs.apply(qv, dv)

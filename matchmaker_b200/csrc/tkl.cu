@@ -1,0 +1,408 @@
+// TKL (SIGIR'20) interaction stage: per-chunk cosine + RBF kernels, sliding-window (30, stride 2) kernel
+// pooling with learned saturation, window scores, and the greedy top-3 "hills" selection.
+//
+// Reference arithmetic: matchmaker/models/published/sigir20_tkl.py:180-286.  The reference scatters the
+// per-chunk activations into a zero tensor [B*C, Lq, 40, K], re-assembles [B, Lq, C*40, K] (450 MB at
+// BASELINE config 5) and runs two strided window reductions that each re-read it 15 times.  Here one CTA
+// walks a document segment chunk by chunk, keeps the activations of the last 40 position PAIRS in a
+// shared-memory ring (a window of 30 positions at stride 2 is exactly 15 consecutive pairs), finishes
+// every window as soon as its last pair is known, and writes only the window score [B, W].
+//
+// Exact-zero semantics the reference depends on are preserved: a position counts towards the window
+// "length" iff the sum of its K activations is != 0 (sigir20_tkl.py:210), windows whose score is exactly
+// 0 become the -9900 sentinel (:257), and window sums are formed directly from the activations (no
+// prefix-difference tricks that would leave round-off residue in empty windows).
+#include <algorithm>
+
+#include "host_util.cuh"
+#include "masks.cuh"
+
+namespace mmb {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kChunk = 40;      // sigir20_tkl.py:52
+constexpr int kWindow = 30;     // :56
+constexpr int kPairsPerChunk = kChunk / 2;
+constexpr int kWinPairs = kWindow / 2;  // 15
+constexpr int kRing = 2 * kPairsPerChunk;  // pairs kept: previous + current chunk
+constexpr int kMaxLq = 40;
+constexpr float kTiny = 1e-13f;
+constexpr float kClamp = 1e-10f;
+
+struct TklParams {
+  const float* q;            // [B, Lq, D] contextualised (masked) query embeddings
+  const void* q_mask;        // [B, Lq]
+  const float* chunks;       // [Nc, 40, D] contextualised packed chunks (overlap removed)
+  const void* chunk_mask;    // [Nc, 40]
+  const int32_t* slot_to_packed;  // [B*C], -1 = chunk slot skipped by the packing (all padding)
+  const float* mu;
+  const float* sigma;
+  const float* dense_w;      // [K]
+  const float* sat_red_w;    // [D]   ("embedding" saturation) or nullptr
+  const float* sat_params;   // embedding: 13 floats (see host); log: kernel_mult0[K]
+  float* window_score;       // [B, W]
+  int64_t B;
+  int32_t Lq, D, C, K, W, mask_dtype, saturation;  // saturation: 0 = embedding, 1 = log
+  int32_t segs, chunks_per_seg;
+};
+
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2a(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__host__ __device__ inline int tkl_row_stride(int D) {
+  int dp = (D + 3) & ~3;
+  if (((dp >> 2) & 1) == 0) dp += 4;
+  return dp;
+}
+
+// rows -> smem, L2-normalised; one warp per row.  Optionally dots the RAW row with `red_w`.
+__device__ __forceinline__ void load_rows_norm(const float* __restrict__ src, int nrows_valid, int nrows, int D, int dp,
+                                               float* __restrict__ dst, const float* __restrict__ red_w,
+                                               float* __restrict__ red_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int d4 = D >> 2;
+  for (int r = warp; r < nrows; r += nw) {
+    float* drow = dst + (size_t)r * dp;
+    if (r < nrows_valid) {
+      const float4* srow = reinterpret_cast<const float4*>(src + (size_t)r * D);
+      float ss = 0.f, rd = 0.f;
+      for (int c = lane; c < d4; c += 32) {
+        const float4 v = __ldg(srow + c);
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+        if (red_w) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(red_w) + c);
+          rd = fmaf(v.x, w.x, rd); rd = fmaf(v.y, w.y, rd); rd = fmaf(v.z, w.z, rd); rd = fmaf(v.w, w.w, rd);
+        }
+        *reinterpret_cast<float4*>(drow + 4 * c) = v;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        rd += __shfl_xor_sync(0xffffffffu, rd, o);
+      }
+      const float inv = 1.0f / (sqrtf(ss) + kTiny);
+      __syncwarp();
+      for (int c = lane; c < d4; c += 32) {
+        float4 v = *reinterpret_cast<float4*>(drow + 4 * c);
+        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+        *reinterpret_cast<float4*>(drow + 4 * c) = v;
+      }
+      if (lane == 0 && red_out) red_out[r] = rd;
+    } else {
+      for (int c = lane; c < d4; c += 32) *reinterpret_cast<float4*>(drow + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane == 0 && red_out) red_out[r] = 0.f;
+    }
+  }
+}
+
+// cos[40 x 40]: 200 threads, each 4 query rows (ti + 10 r) x 2 chunk rows (tj + 20 s).
+__device__ __forceinline__ void cos_40x40(const float* __restrict__ qs, const float* __restrict__ ds, int D, int dp,
+                                          float* __restrict__ cs /* [40][41] */) {
+  const int t = threadIdx.x;
+  if (t >= 200) return;
+  const int ti = t % 10, tj = t / 10;
+  float acc[4][2] = {};
+  const int d4 = D >> 2;
+  for (int c = 0; c < d4; ++c) {
+    float4 qv[4], dv[2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) qv[r] = *reinterpret_cast<const float4*>(qs + (size_t)(ti + 10 * r) * dp + 4 * c);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) dv[s] = *reinterpret_cast<const float4*>(ds + (size_t)(tj + 20 * s) * dp + 4 * c);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        acc[r][s] = fmaf(qv[r].x, dv[s].x, acc[r][s]);
+        acc[r][s] = fmaf(qv[r].y, dv[s].y, acc[r][s]);
+        acc[r][s] = fmaf(qv[r].z, dv[s].z, acc[r][s]);
+        acc[r][s] = fmaf(qv[r].w, dv[s].w, acc[r][s]);
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) cs[(ti + 10 * r) * 41 + tj + 20 * s] = acc[r][s];
+}
+
+template <int KB>
+__global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
+  extern __shared__ __align__(16) float sm[];
+  const int D = P.D, dp = tkl_row_stride(D), Lq = P.Lq, K = P.K;
+  float* qs = sm;                                   // [40][dp]  normalised query rows
+  float* ds = qs + (size_t)kMaxLq * dp;             // [40][dp]  normalised chunk rows; later scratch T[20][40][KB]
+  float* cs = ds + (size_t)kChunk * dp;             // [40][41]
+  float* U = cs + kMaxLq * 41;                      // [40 i][kRing][KB] pair sums of activations
+  float* Z = U + (size_t)kMaxLq * kRing * KB;       // [40 i][kRing] non-zero position counts per pair
+  float* red = Z + kMaxLq * kRing;                  // [40] sat_emb_reduce1(q_i)
+  float* qm_s = red + kMaxLq;                       // [40]
+  float* dm_s = qm_s + kMaxLq;                      // [40]
+  float* mu_s = dm_s + kChunk;                      // [KB]
+  float* a_s = mu_s + KB;
+  float* w_s = a_s + KB;
+  float* km_s = w_s + KB;                           // kernel_mult0 (log saturation)
+  float* sp = km_s + KB;                            // [16] saturation scalars
+  float* pk = sp + 16;                              // [20][KB] per-kernel sums over query rows
+  const int t = threadIdx.x;
+
+  if (t < KB) {
+    const bool ok = t < K;
+    mu_s[t] = ok ? P.mu[t] : 0.f;
+    a_s[t] = ok ? sqrtf(0.5f * 1.4426950408889634f) / P.sigma[t] : 0.f;
+    w_s[t] = ok ? P.dense_w[t] : 0.f;
+    km_s[t] = (ok && P.saturation == 1) ? P.sat_params[t] : 1.f;
+  }
+  if (t < 16) sp[t] = (P.saturation == 0 && t < 13) ? P.sat_params[t] : 0.f;
+
+  const int64_t n_items = P.B * P.segs;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int64_t b = item / P.segs;
+    const int seg = (int)(item % P.segs);
+    const int c_first = seg * P.chunks_per_seg;
+    const int c_last = min(P.C, c_first + P.chunks_per_seg);
+    if (c_first >= c_last) continue;
+    __syncthreads();
+    load_rows_norm(P.q + b * (int64_t)Lq * D, Lq, kMaxLq, D, dp, qs, P.saturation == 0 ? P.sat_red_w : nullptr, red);
+    if (t < kMaxLq) qm_s[t] = (t < Lq && mask_at(P.q_mask, P.q_mask ? P.mask_dtype : 0, b * (int64_t)Lq + t)) ? 1.f : 0.f;
+    // one halo chunk in front supplies the 14 pairs that windows ending in this segment reach back to
+    for (int c = max(0, c_first - 1); c < c_last; ++c) {
+      const int pk_idx = P.slot_to_packed[b * P.C + c];
+      __syncthreads();
+      if (pk_idx >= 0) {
+        load_rows_norm(P.chunks + (int64_t)pk_idx * kChunk * D, kChunk, kChunk, D, dp, ds, nullptr, nullptr);
+        if (t < kChunk) dm_s[t] = mask_at(P.chunk_mask, P.chunk_mask ? P.mask_dtype : 0, (int64_t)pk_idx * kChunk + t) ? 1.f : 0.f;
+        __syncthreads();
+        cos_40x40(qs, ds, D, dp, cs);
+        __syncthreads();
+      }
+      // activations of this chunk's 20 position pairs -> ring
+      for (int e = t; e < kMaxLq * kPairsPerChunk; e += kThreads) {
+        const int i = e / kPairsPerChunk, ul = e % kPairsPerChunk;
+        const int slot = (c * kPairsPerChunk + ul) % kRing;
+        float* u = U + ((size_t)i * kRing + slot) * KB;
+        float nz = 0.f;
+        if (pk_idx >= 0 && i < Lq) {
+          const int p0 = 2 * ul, p1 = p0 + 1;
+          const float c0 = cs[i * 41 + p0], c1 = cs[i * 41 + p1];
+          const bool m0 = dm_s[p0] != 0.f, m1 = dm_s[p1] != 0.f;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < KB; ++k) {
+            const float x0 = (c0 - mu_s[k]) * a_s[k], x1 = (c1 - mu_s[k]) * a_s[k];
+            const float v0 = (m0 && k < K) ? ex2a(-x0 * x0) : 0.f;
+            const float v1 = (m1 && k < K) ? ex2a(-x1 * x1) : 0.f;
+            s0 += v0; s1 += v1;
+            u[k] = v0 + v1;
+          }
+          nz = (s0 != 0.f ? 1.f : 0.f) + (s1 != 0.f ? 1.f : 0.f);  // sigir20_tkl.py:210
+        } else {
+#pragma unroll
+          for (int k = 0; k < KB; ++k) u[k] = 0.f;
+        }
+        Z[i * kRing + slot] = nz;
+      }
+      __syncthreads();
+      if (c < c_first) continue;  // halo chunk: nothing to finish
+      // windows whose last pair lies in this chunk: w + 14 in [20c, 20c+20)
+      const int w_lo = max(0, c * kPairsPerChunk - (kWinPairs - 1));
+      const int w_hi = min(P.W, c * kPairsPerChunk + kPairsPerChunk - (kWinPairs - 1));
+      const int nw = w_hi - w_lo;
+      if (nw <= 0) continue;
+      float* T = ds;  // scratch [20][40][KB] (the chunk rows are no longer needed)
+      for (int e = t; e < nw * kMaxLq; e += kThreads) {
+        const int wl = e / kMaxLq, i = e % kMaxLq;
+        const int w = w_lo + wl;
+        float S[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) S[k] = 0.f;
+        float len = 0.f;
+        for (int u = 0; u < kWinPairs; ++u) {
+          const int slot = (w + u) % kRing;
+          const float* up = U + ((size_t)i * kRing + slot) * KB;
+#pragma unroll
+          for (int k = 0; k < KB; ++k) S[k] += up[k];
+          len += Z[i * kRing + slot];
+        }
+        const float gate = (i < Lq && qm_s[i] != 0.f && len > 0.f) ? 1.f : 0.f;  // :248
+        float* Tp = T + ((size_t)wl * kMaxLq + i) * KB;
+        if (P.saturation == 0) {
+          // LayerNorm over the pair (reduce(q_i), len), then three Linear(2,1) (:224-234)
+          const float a0 = red[i], a1 = len;
+          const float mean = (a0 + a1) * 0.5f;
+          const float d0 = a0 - mean, d1 = a1 - mean;
+          const float rstd = rsqrtf((d0 * d0 + d1 * d1) * 0.5f + 1e-5f);
+          const float y0 = d0 * rstd * sp[0] + sp[2], y1 = d1 * rstd * sp[1] + sp[3];
+          const float sat1 = y0 * sp[4] + y1 * sp[5] + sp[6];
+          const float sat2 = 1.0f / (y0 * sp[7] + y1 * sp[8] + sp[9]);
+          const float sat3 = y0 * sp[10] + y1 * sp[11] + sp[12];
+#pragma unroll
+          for (int k = 0; k < KB; ++k) {
+            const float pw = ex2a(sat2 * lg2a(fmaxf(S[k], kClamp)));
+            Tp[k] = (k < K) ? (sat1 * pw - sat3) * gate : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < KB; ++k) Tp[k] = (k < K) ? logf(fmaxf(S[k] * km_s[k], kClamp)) * gate : 0.f;  // :246
+        }
+      }
+      __syncthreads();
+      for (int e = t; e < nw * KB; e += kThreads) {  // per_kernel = sum over query rows (:249)
+        const int wl = e / KB, k = e % KB;
+        float s = 0.f;
+        for (int i = 0; i < Lq; ++i) s += T[((size_t)wl * kMaxLq + i) * KB + k];
+        pk[wl * KB + k] = s;
+      }
+      __syncthreads();
+      if (t < nw) {  // dense (:251-252)
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) s = fmaf(pk[t * KB + k], w_s[k], s);
+        P.window_score[b * P.W + w_lo + t] = s;
+      }
+    }
+  }
+}
+
+// One warp per document: sentinel, 3 greedy hills, neighbours, weighted sum (sigir20_tkl.py:254-286).
+__global__ void __launch_bounds__(128) tkl_hills_kernel(float* __restrict__ window_score, const float* __restrict__ chunk_scoring,
+                                                        int64_t* __restrict__ top_idx, float* __restrict__ top15,
+                                                        float* __restrict__ score, int64_t B, int W) {
+  extern __shared__ float work[];  // [4 warps][W]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * 4 + warp;
+  if (b >= B) return;
+  float* ws = window_score + b * W;
+  float* wk = work + (size_t)warp * W;
+  for (int w = lane; w < W; w += 32) {
+    float v = ws[w];
+    if (v == 0.f) v = -9900.f;  // :257
+    ws[w] = v;
+    wk[w] = v;
+  }
+  __syncwarp();
+  int best[3];
+  for (int c = 0; c < 3; ++c) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int w = lane; w < W; w += 32) {
+      const float v = wk[w];
+      if (v > bv) { bv = v; bi = w; }  // ascending scan keeps the first maximum
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    best[c] = bi;
+    for (int w = lane; w < W; w += 32)
+      if (fabsf((float)(w - bi)) < 15.0f) wk[w] = -10001.f - (float)c;  // |r - best| < window/2 (:270-271)
+    __syncwarp();
+  }
+  if (lane < 15) {
+    const int c = lane % 3, off_sel = lane / 3;  // cat([idx, idx-1, idx+1, idx-2, idx+2], dim=1) (:274)
+    const int off = off_sel == 0 ? 0 : (off_sel == 1 ? -1 : (off_sel == 2 ? 1 : (off_sel == 3 ? -2 : 2)));
+    int idx = best[c] + off;
+    idx = idx < 0 ? 0 : (idx >= W ? W - 1 : idx);
+    float v = ws[idx];
+    if (v <= -9900.f) v = 0.f;  // :281
+    top15[b * 15 + lane] = v;
+  }
+  if (lane < 3) top_idx[b * 3 + lane] = best[lane];
+  __syncwarp();
+  float part = lane < 15 ? top15[b * 15 + lane] * chunk_scoring[lane] : 0.f;
+  // fixed-order sum over the 15 terms (lane 0 adds them sequentially)
+  float tot = 0.f;
+  for (int l = 0; l < 15; ++l) tot += __shfl_sync(0xffffffffu, part, l);
+  if (lane == 0) score[b] = tot;
+  __syncwarp();
+  for (int w = lane; w < W; w += 32)
+    if (ws[w] <= -9900.f) ws[w] = 0.f;  // :284 (the reference's returned "orig_score")
+}
+
+}  // namespace
+
+}  // namespace mmb
+
+extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, const float* chunks, const void* chunk_mask,
+                                        const int32_t* slot_to_packed, const float* mu, const float* sigma,
+                                        const float* dense_w, const float* sat_red_w, const float* sat_params,
+                                        float* window_score, int64_t B, int32_t Lq, int32_t D, int32_t C, int32_t K,
+                                        int32_t saturation, int32_t mask_dtype, void* stream_) {
+  using namespace mmb;
+  MMB_REQUIRE(q && chunks && slot_to_packed && mu && sigma && dense_w && sat_params && window_score, "null pointer");
+  MMB_REQUIRE(B >= 0 && Lq >= 1 && Lq <= kMaxLq, "TKL kernel supports 1 <= Lq <= 40");
+  MMB_REQUIRE(D > 0 && D % 4 == 0, "embedding dim must be a multiple of 4");
+  MMB_REQUIRE(C >= 1 && K >= 1 && K <= 16, "need C >= 1 and K <= 16");
+  MMB_REQUIRE(saturation == 0 || saturation == 1, "saturation: 0 = embedding, 1 = log");
+  MMB_REQUIRE(saturation == 1 || sat_red_w != nullptr, "embedding saturation needs sat_emb_reduce1 weights");
+  if (q_mask || chunk_mask) MMB_REQUIRE(mask_dtype_size(mask_dtype) != 0, "unknown mask dtype");
+  if (B == 0) return MMB200_OK;
+  DeviceInfo dev;
+  if (int rc = current_device_info(&dev)) return rc;
+  if (!is_sm100(dev)) {
+    set_error("matchmaker_b200 kernels are built for sm_100a only");
+    return MMB200_ERR_UNSUPPORTED;
+  }
+  TklParams P{};
+  P.q = q; P.q_mask = q_mask; P.chunks = chunks; P.chunk_mask = chunk_mask; P.slot_to_packed = slot_to_packed;
+  P.mu = mu; P.sigma = sigma; P.dense_w = dense_w; P.sat_red_w = sat_red_w; P.sat_params = sat_params;
+  P.window_score = window_score; P.B = B; P.Lq = Lq; P.D = D; P.C = C; P.K = K; P.mask_dtype = mask_dtype;
+  P.saturation = saturation;
+  P.W = (C * kChunk - kWindow) / 2 + 1;
+  // split long documents over several CTAs when there are fewer documents than SMs
+  int segs = 1;
+  if (B < dev.sm_count) segs = std::min<int>(C, std::max<int>(1, (int)((2 * dev.sm_count + B - 1) / B)));
+  P.chunks_per_seg = (C + segs - 1) / segs;
+  P.segs = (C + P.chunks_per_seg - 1) / P.chunks_per_seg;
+  const int KB = K <= 12 ? 12 : 16;
+  const int dp = tkl_row_stride(D);
+  const size_t floats = (size_t)2 * kMaxLq * dp + kMaxLq * 41 + (size_t)kMaxLq * kRing * KB + kMaxLq * kRing + 3 * kMaxLq +
+                        4 * KB + 16 + 20 * KB;
+  const size_t need = std::max(floats, (size_t)kMaxLq * dp + (size_t)20 * kMaxLq * KB) * sizeof(float);
+  if (need > (size_t)dev.max_smem_optin || (size_t)20 * kMaxLq * KB > (size_t)kChunk * dp) {
+    set_error("TKL kernel: shape does not fit the shared-memory plan (needs D >= 20*K and ~200 KB for D=300)");
+    return MMB200_ERR_UNSUPPORTED;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int grid = (int)std::min<int64_t>(B * P.segs, (int64_t)dev.sm_count * 2);
+  if (KB == 12) {
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_window_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    tkl_window_kernel<12><<<grid, kThreads, need, stream>>>(P);
+  } else {
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_window_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    tkl_window_kernel<16><<<grid, kThreads, need, stream>>>(P);
+  }
+  MMB_CHECK_CUDA(cudaGetLastError());
+  return MMB200_OK;
+}
+
+extern "C" int mmb200_tkl_top_hills(float* window_score, const float* chunk_scoring, int64_t* top_idx, float* top15,
+                                    float* score, int64_t B, int32_t W, void* stream_) {
+  using namespace mmb;
+  MMB_REQUIRE(window_score && chunk_scoring && top_idx && top15 && score, "null pointer");
+  MMB_REQUIRE(W >= 3, "need at least 3 windows");
+  if (B == 0) return MMB200_OK;
+  DeviceInfo dev;
+  if (int rc = current_device_info(&dev)) return rc;
+  if (!is_sm100(dev)) {
+    set_error("matchmaker_b200 kernels are built for sm_100a only");
+    return MMB200_ERR_UNSUPPORTED;
+  }
+  const size_t smem = (size_t)4 * W * sizeof(float);
+  MMB_REQUIRE(smem <= (size_t)dev.max_smem_optin, "too many windows for the hills kernel");
+  MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_hills_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tkl_hills_kernel<<<(unsigned)((B + 3) / 4), 128, smem, static_cast<cudaStream_t>(stream_)>>>(
+      window_score, chunk_scoring, top_idx, top15, score, B, W);
+  MMB_CHECK_CUDA(cudaGetLastError());
+  return MMB200_OK;
+}

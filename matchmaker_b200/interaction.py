@@ -241,3 +241,19 @@ def kernel_pool_bwd(q, d, q_mask, d_mask, mu, sigma, weight, alpha, per_kernel_q
                                         B, Lq, Ld, D, K, float(log_scale), mcode, _stream(dev))
     _lib.check(rc, "mmb200_kernel_pool_bwd")
     return gq, gd, (ga if alpha is not None else None), gw
+
+
+def dot_pairs(qv: torch.Tensor, dv: torch.Tensor) -> torch.Tensor:
+    """score[b] = <qv[b], dv[b]> in fp32 (bert_dot.py:62).  qv, dv [B, dim], same dtype."""
+    dev = _require_cuda(qv, dv)
+    if qv.dtype != dv.dtype or qv.dtype not in _DTYPES or qv.shape != dv.shape or qv.dim() != 2:
+        raise _lib.MatchmakerB200Error(f"dot_pairs expects two [B,dim] tensors of one dtype, got {tuple(qv.shape)} "
+                                       f"{qv.dtype} / {tuple(dv.shape)} {dv.dtype}")
+    qv, dv = qv.contiguous(), dv.contiguous()
+    out = torch.empty(qv.shape[0], dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.mmb200_dot_pairs(_ptr(qv), _ptr(dv), _ptr(out), qv.shape[0], qv.shape[1], _DTYPES[qv.dtype],
+                                  _stream(dev))
+    _lib.check(rc, "mmb200_dot_pairs")
+    return out
