@@ -49,54 +49,69 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every ~5 ms through NVML while the timed regions run (nvidia-smi
+    -lms 200 is too coarse: the 20-step timed region of this kernel lasts ~10 ms)."""
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    pass
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
+    def _run(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag.is_set():
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = get_reasons(self.h)
+                self.samples.append((time.perf_counter(), clk, rs))
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                break
+            time.sleep(0.005)
+
+    def stop(self, windows):
+        """windows: list of (t0, t1) perf_counter intervals that were timed regions."""
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)]
+        used = inside if inside else self.samples
+        clocks = [c for _, c, _ in used]
+        reasons = set()
+        for _, _, r in used:
+            for n, bit in names.items():
+                if r & bit:
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(clocks) if clocks else None, "sm_max_mhz": self.smax,
+                "samples_in_timed_regions": len(inside), "samples_total": len(self.samples),
+                "reasons": sorted(reasons), "how": "NVML poll every 5 ms; timed regions = value loop + e2e loop"}
 
 
 def make_inputs(shard: int):
@@ -217,6 +232,7 @@ def main():
     kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_val0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         kern_ev[i][0].record()
@@ -226,7 +242,7 @@ def main():
             sharding.topk_all_gather_merge(s.view(N_QUERIES, DOCS_PER_QUERY), TOPK, doc_id_base)
     e1.record()
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
+    t_val1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
     kern_ms = statistics.mean(a.elapsed_time(b) for a, b in kern_ev)
     t = torch.tensor([ms_total, kern_ms], device=dev, dtype=torch.float64)
@@ -247,7 +263,9 @@ def main():
     for _ in range(e2e_steps):
         out = interaction.maxsim_host(hq, hd, hqm, hdm, docs_per_query=DOCS_PER_QUERY, device=dev)  # synchronous
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t_e2e1 = time.perf_counter()
+    clocks = sampler.stop([(t_val0, t_val1), (t0, t_e2e1)]) if rank == 0 else None
+    e2e_s = (t_e2e1 - t0) / e2e_steps
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

@@ -162,6 +162,40 @@ MMB200_API int mmb200_kernel_pool_bwd(const float* q, const float* d, const void
 MMB200_API int mmb200_dot_pairs(const void* q, const void* d, float* out, int64_t B, int32_t dim,
                                 int32_t dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * TKL (long documents): per-chunk cosine + RBF kernels, sliding-window kernel pooling with learned
+ * saturation, window scores; then the greedy top-3 window selection.
+ *
+ * Replaces: TKL_sigir20.forward   matchmaker/models/published/sigir20_tkl.py:180-252 (window scores)
+ *                                 matchmaker/models/published/sigir20_tkl.py:254-286 (top hills)
+ * Chunking / packing / contextualisation (:136-175) stay in PyTorch, as in the reference.
+ *
+ * q             [B, Lq, D] f32  contextualised, masked query embeddings (Lq <= 40)
+ * q_mask        [B, Lq] (`mask_dtype`)
+ * chunks        [Nc, 40, D] f32 contextualised packed chunks, overlap removed (:174)
+ * chunk_mask    [Nc, 40]
+ * slot_to_packed [B*C] int32: packed index of chunk slot (b, c), -1 where the reference's
+ *               `packed_indices` (:159) dropped the chunk
+ * mu, sigma, dense_w [K] (K <= 16)
+ * saturation 0 ("embedding", :222-234): sat_red_w [D] = sat_emb_reduce1.weight, sat_params[13] =
+ *               {sat_normer.weight[2], sat_normer.bias[2], saturation_linear.weight[2], .bias,
+ *                saturation_linear2.weight[2], .bias, saturation_linear3.weight[2], .bias}
+ * saturation 1 ("log", :245-246): sat_params[K] = kernel_mult[0]
+ * window_score  [B, W] f32 out, W = (C*40 - 30)/2 + 1  (raw dense output, sentinel not yet applied)
+ * ------------------------------------------------------------------------------------------ */
+MMB200_API int mmb200_tkl_window_scores(const float* q, const void* q_mask, const float* chunks,
+                                        const void* chunk_mask, const int32_t* slot_to_packed,
+                                        const float* mu, const float* sigma, const float* dense_w,
+                                        const float* sat_red_w, const float* sat_params,
+                                        float* window_score, int64_t B, int32_t Lq, int32_t D, int32_t C,
+                                        int32_t K, int32_t saturation, int32_t mask_dtype, void* stream);
+
+/* window_score [B,W] in/out: on return holds the reference's "orig_score" (exact zeros -> -9900
+ * sentinel during selection, written back as 0).  chunk_scoring [15]; top_idx [B,3] int64;
+ * top15 [B,15] ("top_k_non_overlapping"); score [B]. */
+MMB200_API int mmb200_tkl_top_hills(float* window_score, const float* chunk_scoring, int64_t* top_idx,
+                                    float* top15, float* score, int64_t B, int32_t W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

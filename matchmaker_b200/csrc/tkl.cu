@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
   extern __shared__ __align__(16) float sm[];
   const int D = P.D, dp = tkl_row_stride(D), Lq = P.Lq, K = P.K;
   float* qs = sm;                                   // [40][dp]  normalised query rows
-  float* ds = qs + (size_t)kMaxLq * dp;             // [40][dp]  normalised chunk rows; later scratch T[20][40][KB]
+  float* ds = qs + (size_t)kMaxLq * dp;             // [40][dp]  normalised chunk rows
   float* cs = ds + (size_t)kChunk * dp;             // [40][41]
   float* U = cs + kMaxLq * 41;                      // [40 i][kRing][KB] pair sums of activations
   float* Z = U + (size_t)kMaxLq * kRing * KB;       // [40 i][kRing] non-zero position counts per pair
@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
   float* km_s = w_s + KB;                           // kernel_mult0 (log saturation)
   float* sp = km_s + KB;                            // [16] saturation scalars
   float* pk = sp + 16;                              // [20][KB] per-kernel sums over query rows
+  float* T = pk + 20 * KB;                          // [20 windows][40][KB] saturated activations
   const int t = threadIdx.x;
 
   if (t < KB) {
@@ -218,7 +219,6 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
       const int w_hi = min(P.W, c * kPairsPerChunk + kPairsPerChunk - (kWinPairs - 1));
       const int nw = w_hi - w_lo;
       if (nw <= 0) continue;
-      float* T = ds;  // scratch [20][40][KB] (the chunk rows are no longer needed)
       for (int e = t; e < nw * kMaxLq; e += kThreads) {
         const int wl = e / kMaxLq, i = e % kMaxLq;
         const int w = w_lo + wl;
@@ -366,11 +366,10 @@ extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
   P.segs = (C + P.chunks_per_seg - 1) / P.chunks_per_seg;
   const int KB = K <= 12 ? 12 : 16;
   const int dp = tkl_row_stride(D);
-  const size_t floats = (size_t)2 * kMaxLq * dp + kMaxLq * 41 + (size_t)kMaxLq * kRing * KB + kMaxLq * kRing + 3 * kMaxLq +
-                        4 * KB + 16 + 20 * KB;
-  const size_t need = std::max(floats, (size_t)kMaxLq * dp + (size_t)20 * kMaxLq * KB) * sizeof(float);
-  if (need > (size_t)dev.max_smem_optin || (size_t)20 * kMaxLq * KB > (size_t)kChunk * dp) {
-    set_error("TKL kernel: shape does not fit the shared-memory plan (needs D >= 20*K and ~200 KB for D=300)");
+  const size_t need = ((size_t)2 * kMaxLq * dp + kMaxLq * 41 + (size_t)kMaxLq * kRing * KB + kMaxLq * kRing + 3 * kMaxLq +
+                       4 * KB + 16 + 20 * KB + (size_t)20 * kMaxLq * KB) * sizeof(float);
+  if (need > (size_t)dev.max_smem_optin) {
+    set_error("TKL kernel: embedding dim / kernel count too large for the shared-memory plan (D=300 fits with K <= 12)");
     return MMB200_ERR_UNSUPPORTED;
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

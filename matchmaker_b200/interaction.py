@@ -257,3 +257,57 @@ def dot_pairs(qv: torch.Tensor, dv: torch.Tensor) -> torch.Tensor:
                                   _stream(dev))
     _lib.check(rc, "mmb200_dot_pairs")
     return out
+
+
+TKL_CHUNK, TKL_WINDOW = 40, 30
+
+
+def tkl_window_scores(q_ctx: torch.Tensor, q_mask: torch.Tensor, doc_chunks: torch.Tensor, chunk_mask: torch.Tensor,
+                      packed_indices: torch.Tensor, chunk_pieces: int, mu: torch.Tensor, sigma: torch.Tensor,
+                      dense_weight: torch.Tensor, saturation: str, sat_params: torch.Tensor,
+                      sat_red_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Window scores [B, W] of the TKL interaction stage (sigir20_tkl.py:180-252).
+
+    ``packed_indices`` [B*C] bool is the reference's chunk packing mask (:159); ``doc_chunks`` [Nc,40,D] /
+    ``chunk_mask`` [Nc,40] are the packed, contextualised chunks without overlap (:174-175)."""
+    dev = _require_cuda(q_ctx, q_mask, doc_chunks, chunk_mask, packed_indices, mu, sigma, dense_weight, sat_params)
+    q_ctx = q_ctx.float().contiguous()
+    doc_chunks = doc_chunks.float().contiguous()
+    B, Lq, D = q_ctx.shape
+    C = int(chunk_pieces)
+    if packed_indices.numel() != B * C or doc_chunks.shape[1] != TKL_CHUNK:
+        raise _lib.MatchmakerB200Error("tkl_window_scores: inconsistent chunk packing")
+    pk = packed_indices.reshape(-1).to(torch.int32)
+    slot_to_packed = (torch.cumsum(pk, 0, dtype=torch.int32) - 1).masked_fill(pk == 0, -1).contiguous()
+    q_mask, chunk_mask, mcode = _common_mask_dtype(_prep_mask(q_mask), _prep_mask(chunk_mask))
+    mu, sigma, dense_weight = _f32c(mu).view(-1), _f32c(sigma).view(-1), _f32c(dense_weight).view(-1)
+    sat_params = _f32c(sat_params).view(-1)
+    sat_code = {"embedding": 0, "log": 1}[saturation]
+    red = None if sat_red_weight is None else _f32c(sat_red_weight).view(-1)
+    K = mu.numel()
+    W = (C * TKL_CHUNK - TKL_WINDOW) // 2 + 1
+    out = torch.empty((B, W), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.mmb200_tkl_window_scores(_ptr(q_ctx), _ptr(q_mask), _ptr(doc_chunks), _ptr(chunk_mask),
+                                          _ptr(slot_to_packed), _ptr(mu), _ptr(sigma), _ptr(dense_weight), _ptr(red),
+                                          _ptr(sat_params), _ptr(out), B, Lq, D, C, K, sat_code, mcode, _stream(dev))
+    _lib.check(rc, "mmb200_tkl_window_scores")
+    return out
+
+
+def tkl_top_hills(window_score: torch.Tensor, chunk_scoring: torch.Tensor):
+    """Greedy top-3 windows with +-15 suppression, +-1/+-2 neighbours, weighted sum (sigir20_tkl.py:254-286).
+    Returns (score [B], orig_score [B,W], top_idx [B,3] int64, top15 [B,15]); ``window_score`` is not modified."""
+    dev = _require_cuda(window_score, chunk_scoring)
+    ws = window_score.float().contiguous().clone()
+    B, W = ws.shape
+    top_idx = torch.empty((B, 3), dtype=torch.int64, device=dev)
+    top15 = torch.empty((B, 15), dtype=torch.float32, device=dev)
+    score = torch.empty(B, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.mmb200_tkl_top_hills(_ptr(ws), _ptr(_f32c(chunk_scoring).view(-1)), _ptr(top_idx), _ptr(top15),
+                                      _ptr(score), B, W, _stream(dev))
+    _lib.check(rc, "mmb200_tkl_top_hills")
+    return score, ws, top_idx, top15

@@ -43,12 +43,12 @@ def all_gather_merge(local_scores: torch.Tensor, local_ids: torch.Tensor, k: int
         return rank_topk(local_scores, local_ids, k)
     world = dist.get_world_size(group)
     nq, kl = local_scores.shape
-    gs = torch.empty((world, nq, kl), dtype=local_scores.dtype, device=local_scores.device)
-    gi = torch.empty((world, nq, kl), dtype=local_ids.dtype, device=local_ids.device)
-    dist.all_gather_into_tensor(gs, local_scores.contiguous(), group=group)
+    gs = torch.empty((world * nq, kl), dtype=local_scores.dtype, device=local_scores.device)
+    gi = torch.empty((world * nq, kl), dtype=local_ids.dtype, device=local_ids.device)
+    dist.all_gather_into_tensor(gs, local_scores.contiguous(), group=group)  # rank-major concatenation
     dist.all_gather_into_tensor(gi, local_ids.contiguous(), group=group)
-    cs = gs.permute(1, 0, 2).reshape(nq, world * kl)
-    ci = gi.permute(1, 0, 2).reshape(nq, world * kl)
+    cs = gs.view(world, nq, kl).permute(1, 0, 2).reshape(nq, world * kl)
+    ci = gi.view(world, nq, kl).permute(1, 0, 2).reshape(nq, world * kl)
     return rank_topk(cs, ci, k)
 
 

@@ -1,0 +1,100 @@
+"""TKL interaction kernels vs the golden vectors of the reference's TKL_sigir20 and the oracle."""
+import pytest
+import torch
+
+from conftest import assert_close_rel, load_golden
+from matchmaker_b200 import interaction
+from oracle import interaction_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _sat_args(params, sat):
+    if sat == "embedding":
+        p = torch.cat([params["sat_normer_weight"], params["sat_normer_bias"], params["saturation_linear_weight"],
+                       params["saturation_linear_bias"], params["saturation_linear2_weight"],
+                       params["saturation_linear2_bias"], params["saturation_linear3_weight"],
+                       params["saturation_linear3_bias"]])
+        return p, params["sat_emb_reduce1_weight"]
+    return params["kernel_mult0"], None
+
+
+def _run(g, params, sat):
+    sp, red = _sat_args(params, sat)
+    ws = interaction.tkl_window_scores(g["q_ctx"].to(DEV), g["q_mask"].to(DEV), g["doc_chunks_ctx"].to(DEV),
+                                       g["doc_chunk_mask"].to(DEV), g["packed_indices"].to(DEV), int(g["chunk_pieces"]),
+                                       params["mu"].to(DEV), params["sigma"].to(DEV), params["dense_weight"].to(DEV), sat,
+                                       sp.to(DEV), None if red is None else red.to(DEV))
+    return ws, interaction.tkl_top_hills(ws, params["chunk_scoring"].to(DEV))
+
+
+@pytest.mark.parametrize("sat", ["embedding", "log"])
+def test_golden_tkl(sat):
+    g = load_golden(f"tkl_{sat}")
+    params = {k[3:]: v for k, v in g.items() if k.startswith("p__")}
+    ws, (score, orig, top_idx, top15) = _run(g, params, sat)
+    assert_close_rel(orig, g["orig_score"], what="orig_score")
+    assert torch.equal(top_idx.cpu(), g["top_non_overlapping_idx"]), "top-3 window indices must be bit-exact"
+    assert_close_rel(top15, g["top_k_non_overlapping"], what="top15")
+    assert_close_rel(score, g["score"], what="score")
+    # exact-zero windows (fully padded regions) must come out as exact zeros
+    assert ((orig.cpu() == 0) == (g["orig_score"] == 0)).all()
+
+
+@pytest.mark.parametrize("sat", ["embedding", "log"])
+@pytest.mark.parametrize("shape", [(3, 40, 2000, 64), (2, 7, 95, 32), (150, 12, 400, 32)])
+def test_seeded_vs_oracle(shape, sat):
+    B, Lq, Ld, D = shape
+    g = torch.Generator().manual_seed(Ld + Lq)
+    q = torch.randn(B, Lq, D, generator=g) * 0.4
+    d = torch.randn(B, Ld, D, generator=g) * 0.4
+    q_len = torch.randint(1, Lq + 1, (B,), generator=g)
+    d_len = torch.randint(1, Ld + 1, (B,), generator=g)
+    d_len[0] = Ld
+    qm = (torch.arange(Lq).unsqueeze(0) < q_len.unsqueeze(1)).float()
+    dm = (torch.arange(Ld).unsqueeze(0) < d_len.unsqueeze(1)).float()
+    q, d = q * qm.unsqueeze(-1), d * dm.unsqueeze(-1)
+    cd2, cp2, packed, pieces = O.tkl_chunk_documents(d, dm)
+    chunks = cd2[packed][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous()
+    cmask = cp2[packed][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous()
+    K = 11
+    params = {"mu": torch.tensor([1.0, 0.9, 0.7, 0.5, 0.3, 0.1, -0.1, -0.3, -0.5, -0.7, -0.9]), "sigma": torch.full((K,), 0.1),
+              "dense_weight": torch.randn(K, generator=g) * 0.1, "chunk_scoring": torch.rand(15, generator=g) + 0.5,
+              "sat_emb_reduce1_weight": torch.randn(D, generator=g) * 0.3,
+              "sat_normer_weight": torch.rand(2, generator=g) + 0.5, "sat_normer_bias": torch.randn(2, generator=g) * 0.1,
+              "saturation_linear_weight": torch.randn(2, generator=g) * 0.014, "saturation_linear_bias": torch.tensor([100.0]),
+              "saturation_linear2_weight": torch.randn(2, generator=g) * 0.014, "saturation_linear2_bias": torch.tensor([100.0]),
+              "saturation_linear3_weight": torch.randn(2, generator=g) * 0.014, "saturation_linear3_bias": torch.tensor([100.0]),
+              "kernel_mult0": torch.rand(K, generator=g) + 0.5}
+    ref_score, sec = O.tkl_interaction(q, qm, chunks, cmask, packed, pieces, params, sat)
+    gd = {"q_ctx": q, "q_mask": qm, "doc_chunks_ctx": chunks, "doc_chunk_mask": cmask, "packed_indices": packed,
+          "chunk_pieces": torch.tensor(pieces)}
+    ws, (score, orig, top_idx, top15) = _run(gd, params, sat)
+    assert_close_rel(orig, sec["orig_score"], what="orig_score")
+    same = (top_idx.cpu() == sec["top_non_overlapping_idx"]).all(dim=1)
+    # index ties: a different-but-equal-valued window may be picked only if the scores tie within tolerance
+    for b in (~same).nonzero().flatten().tolist():
+        a = sec["orig_score"][b][top_idx.cpu()[b]]
+        r = sec["orig_score"][b][sec["top_non_overlapping_idx"][b]]
+        assert torch.allclose(a, r, rtol=1e-3), f"doc {b}: picked windows differ beyond tolerance"
+    assert same.float().mean() > 0.9
+    assert_close_rel(score.cpu()[same], ref_score[same], what="score")
+
+
+def test_dropin_class_matches_reference_golden():
+    from matchmaker_b200.rankers.tkl import TKL_sigir20
+    for sat in ("embedding", "log"):
+        g = load_golden(f"tkl_{sat}")
+        emb, heads, layers, ff = [int(x) for x in g["cfg"]]
+        params = {k[3:]: v for k, v in g.items() if k.startswith("p__")}
+        m = TKL_sigir20(emb, params["mu"].tolist(), params["sigma"].tolist(), heads, layers, ff, 2000, True, True, sat)
+        sd = {k[4:]: v for k, v in g.items() if k.startswith("sd__")}
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.startswith("positional_features") for k in missing), (missing, unexpected)
+        m = m.to(DEV).eval()
+        with torch.no_grad():
+            score, sec = m(g["q"].to(DEV), g["d"].to(DEV), g["q_mask"].to(DEV), g["d_mask"].to(DEV),
+                           output_secondary_output=True)
+        assert_close_rel(score, g["score"], rel=2e-3, what=f"TKL class score ({sat})")
+        assert torch.equal(sec["top_non_overlapping_idx"].cpu(), g["top_non_overlapping_idx"])
