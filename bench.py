@@ -2,7 +2,8 @@
 """Benchmark of the interaction-scoring hot path (BASELINE.json metric: query-doc pairs scored / s,
 ColBERT max-sim, dim=128, Lq=32, Ld=180, 64 queries x 1000 docs per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload colbert]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload colbert|tk|knrm|tkl|bert_dot]     (default colbert = the BASELINE metric)
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL).  Prints ONE JSON line on rank 0.
 
@@ -36,6 +37,16 @@ TOPK = 100
 # doc tile Ld*dim*2 + 4 B length + 4 B score + query tile amortised over 1000 docs
 ALG_BYTES_PER_PAIR = LD * DIM * 2 + 4 + 4 + (LQ * DIM * 2) // DOCS_PER_QUERY
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def _tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        except Exception:
+            pass
+    return 1400.0, "fallback (B200_PROFILING.md sustained)"
 
 
 def _peaks():
@@ -114,64 +125,340 @@ class ClockSampler:
                 "reasons": sorted(reasons), "how": "NVML poll every 5 ms; timed regions = value loop + e2e loop"}
 
 
-def make_inputs(shard: int):
-    from oracle import interaction_oracle as O  # input generator only (shared with the tests)
-    return O.synth_colbert_inputs(N_QUERIES, DOCS_PER_QUERY, LQ, LD, DIM, seed=SEED + shard)
+# ------------------------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs).  Each one: synthetic seeded inputs of that config's shape, a GPU step on
+# HBM-resident inputs, an end-to-end step from pinned host buffers, the CPU oracle step, algorithmic bytes.
+# ------------------------------------------------------------------------------------------------------------
+class ColbertWorkload:
+    """BASELINE config 3: ColBERT max-sim, dim=128, Lq=32, Ld=180, 64 queries x 1000 docs per GPU, fp16."""
+    name = "colbert_maxsim"
+    metric = "query-doc pairs scored/sec (ColBERT max-sim d=128)"
+    dtype = "f16"
+    kernel = "maxsim_qm_kernel"
+    bound = "hbm"
+
+    def __init__(self, rank, dev):
+        from matchmaker_b200 import synthetic as O
+        self.dev = dev
+        self.q, self.d, qm, dm = O.synth_colbert_inputs(N_QUERIES, DOCS_PER_QUERY, LQ, LD, DIM, seed=SEED + rank)
+        self.qm, self.dm = qm, dm
+        self.pairs = N_QUERIES * DOCS_PER_QUERY
+        self.alg_bytes = ALG_BYTES_PER_PAIR * self.pairs
+        self.alg_note = "SURVEY 8(d): Ld*dim*2 + 4 + 4 + Lq*dim*2/docs_per_query = %d B/pair" % ALG_BYTES_PER_PAIR
+        self.id_base = rank * self.pairs
+
+    def to_device(self):
+        self.cq, self.cd = self.q.to(self.dev), self.d.to(self.dev)
+        self.cqm, self.cdm = self.qm.bool().to(self.dev), self.dm.bool().to(self.dev)
+
+    def kernel_step(self):
+        from matchmaker_b200 import interaction
+        return interaction.maxsim(self.cq, self.cd, self.cqm, self.cdm, docs_per_query=DOCS_PER_QUERY, impl="tcgen05")
+
+    def exchange(self, s):
+        from matchmaker_b200 import sharding
+        return sharding.topk_all_gather_merge(s.view(N_QUERIES, DOCS_PER_QUERY), TOPK, self.id_base)
+
+    def pin(self):
+        self.h = [t.pin_memory() for t in (self.q, self.d, self.qm.bool(), self.dm.bool())]
+        return sum(x.numel() * x.element_size() for x in self.h)
+
+    def e2e_step(self):
+        from matchmaker_b200 import interaction
+        return interaction.maxsim_host(*self.h, docs_per_query=DOCS_PER_QUERY, device=self.dev)
+
+    e2e_note = ("mmb200_maxsim_fwd_host: pinned host q/d/masks -> chunked H2D overlapped with the kernel -> D2H "
+                "scores; PCIe-bound")
+
+    def cpu_prepare(self):
+        self.q32, self.d32 = self.q.float(), self.d.float()  # dense_retrieval.py:406 upcasts the fp16 storage
+
+    def cpu_step(self):
+        from oracle import interaction_oracle as O
+        with torch.no_grad():
+            return O.maxsim_one_query_many_docs(self.q32, self.d32, self.qm, self.dm, DOCS_PER_QUERY)
+
+    def config(self, n_gpus):
+        return {"workload": self.name, "queries_per_gpu": N_QUERIES, "docs_per_query": DOCS_PER_QUERY, "Lq": LQ,
+                "Ld": LD, "dim": DIM, "storage_dtype": "float16", "mask_dtype": "bool",
+                "pairs_per_step": self.pairs * n_gpus,
+                "sharding": "documents sharded over ranks; per-query top-%d all-gather + merge when N>1" % TOPK,
+                "l2_policy": "inputs larger than L2 (2.95 GB of documents per GPU per step vs 126 MB L2)"}
 
 
-def cpu_oracle_step(q32, d32, qm, dm):
-    from oracle import interaction_oracle as O
-    with torch.no_grad():
-        return O.maxsim_one_query_many_docs(q32, d32, qm, dm, DOCS_PER_QUERY)
+class KernelPoolWorkload:
+    """BASELINE config 2 (TK interaction: Lq=30, Ld=200, D=300, 21 kernels) or config 1 shape (KNRM: Ld=180, 11
+    kernels); op-level: the contextualised embeddings are the inputs.  The batch is enlarged (default 4096 pairs
+    = 16 x the config's batch of 256) so that the inputs (1.1 GB) exceed L2."""
+    bound = "hbm"
+    dtype = "f32"
+
+    def __init__(self, rank, dev, kind):
+        from matchmaker_b200 import synthetic as O
+        from matchmaker_b200.rankers.knrm import kernel_mus, kernel_sigmas
+        self.dev, self.kind = dev, kind
+        if kind == "tk":
+            self.name, self.B, self.Lq, self.Ld, self.D = "tk_kernel_pool", 4096, 30, 200, 300
+            mu, sg = O.tk_21_kernels()
+            self.log_scale, self.alpha = 1.0, torch.linspace(0.5, 1.5, 21)
+        else:
+            self.name, self.B, self.Lq, self.Ld, self.D = "knrm_kernel_pool", 4096, 30, 180, 300
+            mu, sg = kernel_mus(11), kernel_sigmas(11)
+            self.log_scale, self.alpha = 0.01, None
+        self.metric = "query-doc pairs scored/sec (%s cosine + RBF kernel pooling forward, D=300)" % kind.upper()
+        self.kernel = "kernel_pool_fwd_simt"
+        self.mu, self.sigma = torch.tensor(mu), torch.tensor(sg)
+        self.w = torch.linspace(-0.014, 0.014, len(mu))
+        self.q, self.d, self.qm, self.dm = O.synth_kernel_pool_inputs(self.B, self.Lq, self.Ld, self.D, seed=SEED + 10 + rank)
+        self.pairs = self.B
+        per_pair = (self.Lq + self.Ld) * self.D * 4 + (self.Lq + self.Ld) * 4 + 4
+        self.alg_bytes = per_pair * self.B
+        self.alg_note = "SURVEY 8(d): (Lq+Ld)*D*4 + (Lq+Ld)*4 + 4 = %d B/pair" % per_pair
+
+    def to_device(self):
+        d = self.dev
+        self.c = [t.to(d) for t in (self.q, self.d, self.qm, self.dm, self.mu, self.sigma, self.w)]
+        self.calpha = None if self.alpha is None else self.alpha.to(d)
+
+    def kernel_step(self):
+        from matchmaker_b200 import interaction
+        return interaction.kernel_pool(*self.c, alpha=self.calpha, log_scale=self.log_scale)["score"]
+
+    def exchange(self, s):
+        return s  # re-ranking pairs are independent: no data-path collective
+
+    def pin(self):
+        self.h = [t.pin_memory() for t in (self.q, self.d, self.qm, self.dm)]
+        return sum(x.numel() * x.element_size() for x in self.h)
+
+    def e2e_step(self):
+        from matchmaker_b200 import interaction
+        dq, dd, dqm, ddm = [t.to(self.dev, non_blocking=True) for t in self.h]
+        s = interaction.kernel_pool(dq, dd, dqm, ddm, *self.c[4:], alpha=self.calpha, log_scale=self.log_scale)["score"]
+        return s.cpu()
+
+    e2e_note = "pinned host embeddings+masks -> H2D -> mmb200_kernel_pool_fwd -> D2H scores (the eval.py:89-161 pattern)"
+
+    def cpu_prepare(self):
+        self.cpu_n = 256  # the config's own batch size
+
+    def cpu_step(self):
+        from oracle import interaction_oracle as O
+        n = self.cpu_n
+        with torch.no_grad():
+            if self.kind == "tk":
+                return O.kernel_pool_tk(self.q[:n], self.d[:n], self.qm[:n], self.dm[:n], self.mu, self.sigma, self.alpha, self.w)[0]
+            return O.kernel_pool_knrm(self.q[:n], self.d[:n], self.qm[:n], self.dm[:n], self.mu, self.sigma, self.w)[0]
+
+    def config(self, n_gpus):
+        return {"workload": self.name, "pairs_per_gpu": self.B, "Lq": self.Lq, "Ld": self.Ld, "dim": self.D,
+                "kernels": int(self.mu.numel()), "pairs_per_step": self.B * n_gpus,
+                "sharding": "pairs split over ranks, no collective",
+                "l2_policy": "inputs larger than L2 (%.2f GB per GPU per step)" % (self.alg_bytes / 1e9)}
 
 
-def time_cpu_baseline(q, d, qm, dm, budget_s: float = 12.0):
-    """Reference arithmetic (fp32 upcast of the fp16 storage, dense_retrieval.py:406) on the host cores."""
-    q32, d32 = q.float(), d.float()
-    cpu_oracle_step(q32[:4], d32[:4 * DOCS_PER_QUERY], qm[:4], dm[:4 * DOCS_PER_QUERY])  # warm-up
+class TklWorkload:
+    """BASELINE config 5: TKL interaction + window pooling, Lq=40, Ld=2000, D=300, 11 kernels, 16 docs per GPU
+    (128 over 8 GPUs); op-level inputs = contextualised query + packed contextualised chunks."""
+    bound = "hbm"
+    dtype = "f32"
+    name = "tkl_window_pool"
+    metric = "query-doc pairs scored/sec (TKL chunked kernel pooling + window selection, Ld=2000)"
+    kernel = "tkl_window_kernel"
+
+    def __init__(self, rank, dev, B=128):
+        from matchmaker_b200 import synthetic as O
+        from matchmaker_b200.rankers.tkl import chunk_documents
+        self.dev, self.B, self.Lq, self.Ld, self.D = dev, B, 40, 2000, 300
+        g = torch.Generator().manual_seed(SEED + 20 + rank)
+        self.q = torch.randn(B, self.Lq, self.D, generator=g) * 0.4
+        d = torch.randn(B, self.Ld, self.D, generator=g) * 0.4
+        q_len = torch.randint(3, self.Lq + 1, (B,), generator=g)
+        d_len = O.synth_lengths(B, 1100.0, 500.0, 100, self.Ld, g)
+        self.qm = (torch.arange(self.Lq).unsqueeze(0) < q_len.unsqueeze(1)).float()
+        dm = (torch.arange(self.Ld).unsqueeze(0) < d_len.unsqueeze(1)).float()
+        self.q = self.q * self.qm.unsqueeze(-1)
+        d = d * dm.unsqueeze(-1)
+        cd2, cp2, self.packed, self.pieces = chunk_documents(d, dm)
+        self.chunks = cd2[self.packed][:, 5:-5].contiguous()   # overlap removed (sigir20_tkl.py:174)
+        self.cmask = cp2[self.packed][:, 5:-5].contiguous()
+        K = 11
+        self.params = {"mu": torch.tensor([1.0, 0.9, 0.7, 0.5, 0.3, 0.1, -0.1, -0.3, -0.5, -0.7, -0.9]),
+                       "sigma": torch.full((K,), 0.1), "dense_weight": torch.linspace(-0.014, 0.014, K),
+                       "chunk_scoring": torch.ones(15), "sat_emb_reduce1_weight": torch.randn(self.D, generator=g) * 0.05,
+                       "sat_normer_weight": torch.ones(2), "sat_normer_bias": torch.zeros(2),
+                       "saturation_linear_weight": torch.tensor([0.01, -0.01]), "saturation_linear_bias": torch.tensor([100.0]),
+                       "saturation_linear2_weight": torch.tensor([0.005, 0.01]), "saturation_linear2_bias": torch.tensor([100.0]),
+                       "saturation_linear3_weight": torch.tensor([-0.01, 0.005]), "saturation_linear3_bias": torch.tensor([100.0])}
+        p = self.params
+        self.sat = torch.cat([p["sat_normer_weight"], p["sat_normer_bias"], p["saturation_linear_weight"],
+                              p["saturation_linear_bias"], p["saturation_linear2_weight"], p["saturation_linear2_bias"],
+                              p["saturation_linear3_weight"], p["saturation_linear3_bias"]])
+        self.pairs = B
+        per_pair = self.Lq * self.D * 4 + self.Ld * self.D * 4 + 8160
+        self.alg_bytes = int(self.Lq * self.D * 4 * B + self.chunks.numel() * 4 + self.cmask.numel() * 4)
+        self.alg_note = ("actual packed bytes: query + packed chunks + chunk masks (SURVEY 8(d) dense figure: %d "
+                         "B/pair; documents here average %.0f of 2000 tokens)" % (per_pair, d_len.float().mean().item()))
+
+    def to_device(self):
+        d = self.dev
+        p = self.params
+        self.c = dict(q=self.q.to(d), qm=self.qm.to(d), ch=self.chunks.to(d), cm=self.cmask.to(d), pk=self.packed.to(d),
+                      mu=p["mu"].to(d), sg=p["sigma"].to(d), dw=p["dense_weight"].to(d), sat=self.sat.to(d),
+                      red=p["sat_emb_reduce1_weight"].to(d), cs=p["chunk_scoring"].to(d))
+
+    def _run(self, q, qm, ch, cm, pk):
+        from matchmaker_b200 import interaction
+        c = self.c
+        ws = interaction.tkl_window_scores(q, qm, ch, cm, pk, self.pieces, c["mu"], c["sg"], c["dw"], "embedding", c["sat"], c["red"])
+        return interaction.tkl_top_hills(ws, c["cs"])[0]
+
+    def kernel_step(self):
+        c = self.c
+        return self._run(c["q"], c["qm"], c["ch"], c["cm"], c["pk"])
+
+    def exchange(self, s):
+        return s
+
+    def pin(self):
+        self.h = [t.pin_memory() for t in (self.q, self.qm, self.chunks, self.cmask, self.packed)]
+        return sum(x.numel() * x.element_size() for x in self.h)
+
+    def e2e_step(self):
+        dv = [t.to(self.dev, non_blocking=True) for t in self.h]
+        return self._run(*dv).cpu()
+
+    e2e_note = "pinned host contextualised query/chunks -> H2D -> tkl_window_scores + tkl_top_hills -> D2H scores"
+
+    def cpu_prepare(self):
+        self.cpu_n = 8
+
+    def cpu_step(self):
+        from oracle import interaction_oracle as O
+        n = self.cpu_n
+        C = self.pieces
+        pk = self.packed[:n * C]
+        nc = int(pk.sum())
+        with torch.no_grad():
+            return O.tkl_interaction(self.q[:n], self.qm[:n], self.chunks[:nc], self.cmask[:nc], pk, C, self.params, "embedding")[0]
+
+    def config(self, n_gpus):
+        return {"workload": self.name, "docs_per_gpu": self.B, "Lq": self.Lq, "Ld": self.Ld, "dim": self.D, "kernels": 11,
+                "saturation": "embedding", "pairs_per_step": self.B * n_gpus, "sharding": "documents split over ranks",
+                "l2_policy": "inputs larger than L2 (%.2f GB per GPU per step)" % (self.alg_bytes / 1e9)}
+
+
+class BertDotWorkload:
+    """BASELINE config 4: BERT_DOT retrieval scoring, dim=768, 6400 queries x 8.8 M passages over 8 GPUs = 1.1 M
+    passages per GPU (fp16, 1.69 GB), top-100; tensor-core bound."""
+    bound = "tensor"
+    dtype = "f16"
+    name = "bert_dot_flat_ip_topk"
+    metric = "query-passage pairs scored/sec (BERT_DOT exact inner-product top-100, dim=768)"
+    kernel = "flat_ip_tc_kernel"
+
+    def __init__(self, rank, dev, nq=6400, n_pass=1100000, k=100):
+        from matchmaker_b200 import synthetic as O
+        self.dev, self.nq, self.n, self.k, self.dim = dev, nq, n_pass, k, 768
+        self.q, self.p = O.synth_dense_inputs(nq, n_pass, self.dim, seed=SEED + 30, shard_id=rank)
+        self.pairs = nq * n_pass
+        self.flops = 2.0 * nq * n_pass * self.dim
+        self.alg_bytes = n_pass * self.dim * 2 + nq * self.dim * 2
+        self.alg_note = "2*dim FLOP per (query, passage) pair; passages read once (1 536 B each)"
+        self.id_base = rank * n_pass
+
+    def to_device(self):
+        self.cq, self.cp = self.q.to(self.dev), self.p.to(self.dev)
+
+    def kernel_step(self):
+        from matchmaker_b200 import interaction
+        return interaction.flat_ip_topk(self.cq, self.cp, self.k, id_base=self.id_base)
+
+    def exchange(self, si):
+        from matchmaker_b200 import sharding
+        return sharding.all_gather_merge(si[0], si[1], self.k)
+
+    def pin(self):
+        self.h = [self.q.pin_memory()]
+        return self.h[0].numel() * 2
+
+    def e2e_step(self):
+        # the index (passages) is resident, as in FaissIdIndexer; per step the QUERIES travel (dense_retrieval.py:386-391)
+        from matchmaker_b200 import interaction
+        dq = self.h[0].to(self.dev, non_blocking=True)
+        s, i = interaction.flat_ip_topk(dq, self.cp, self.k, id_base=self.id_base)
+        return torch.cat([s.cpu().view(-1), i.cpu().view(-1).float()])
+
+    e2e_note = "index resident in HBM (as faiss); pinned host queries -> H2D -> fused GEMM+top-k -> D2H (scores, ids)"
+
+    def cpu_prepare(self):
+        self.cq32, self.cpn = self.q[:64].float(), 200000  # 64-query x 200 k-passage slab (BASELINE.md section 2)
+
+    def cpu_step(self):
+        with torch.no_grad():
+            s = self.cq32 @ self.p[:self.cpn].float().T
+            return torch.topk(s, self.k, dim=1)
+
+    def cpu_pairs(self):
+        return 64 * self.cpn
+
+    def config(self, n_gpus):
+        return {"workload": self.name, "queries": self.nq, "passages_per_gpu": self.n, "dim": self.dim, "top_k": self.k,
+                "storage_dtype": "float16", "pairs_per_step": self.pairs * n_gpus,
+                "sharding": "passages sharded over ranks; per-query top-k all-gather + merge when N>1",
+                "l2_policy": "passage shard 1.69 GB per GPU, larger than L2"}
+
+
+def make_workload(name, rank, dev):
+    if name == "colbert":
+        return ColbertWorkload(rank, dev)
+    if name in ("tk", "knrm"):
+        return KernelPoolWorkload(rank, dev, name)
+    if name == "tkl":
+        return TklWorkload(rank, dev)
+    if name == "bert_dot":
+        return BertDotWorkload(rank, dev)
+    raise SystemExit("unknown workload " + name)
+
+
+def time_cpu(wl, budget_s=12.0, max_reps=50):
+    wl.cpu_prepare()
+    wl.cpu_step()  # warm-up
     reps, t_total = 0, 0.0
-    while t_total < budget_s and reps < 50:
+    while t_total < budget_s and reps < max_reps:
         t0 = time.perf_counter()
-        cpu_oracle_step(q32, d32, qm, dm)
+        wl.cpu_step()
         t_total += time.perf_counter() - t0
         reps += 1
-    pairs = N_QUERIES * DOCS_PER_QUERY * reps
-    return {"value": pairs / t_total, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{reps} x full workload ({N_QUERIES} queries x {DOCS_PER_QUERY} docs), torch CPU fp32, "
-                      f"{torch.get_num_threads()} threads of {os.cpu_count()} logical cores"}
-
-
-def config_dict(n_gpus):
-    return {"workload": "colbert_maxsim", "queries_per_gpu": N_QUERIES, "docs_per_query": DOCS_PER_QUERY,
-            "Lq": LQ, "Ld": LD, "dim": DIM, "storage_dtype": "float16", "mask_dtype": "bool",
-            "pairs_per_step": N_QUERIES * DOCS_PER_QUERY * n_gpus,
-            "sharding": "documents sharded over ranks; per-query top-%d all-gather + merge when N>1" % TOPK,
-            "l2_policy": "inputs larger than L2 (2.95 GB of documents per GPU per step vs 126 MB L2)"}
+    per = wl.cpu_pairs() if hasattr(wl, "cpu_pairs") else (getattr(wl, "cpu_n", None) or wl.pairs)
+    return {"value": per * reps / t_total, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d x %d pairs of this workload through the oracle (torch CPU fp32, %d threads of %d logical cores)"
+                      % (reps, per, torch.get_num_threads(), os.cpu_count())}
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU PyTorch path (oracle port) on this host, rank 0 only."""
     if rank != 0:
         return
-    q, d, qm, dm = make_inputs(0)
-    q32, d32 = q.float(), d.float()
+    wl = make_workload(args.workload, 0, torch.device("cpu"))
+    wl.cpu_prepare()
     for _ in range(args.warmup):
-        cpu_oracle_step(q32, d32, qm, dm)
+        wl.cpu_step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_oracle_step(q32, d32, qm, dm)
+        wl.cpu_step()
     dt = time.perf_counter() - t0
-    pairs = N_QUERIES * DOCS_PER_QUERY
-    v = pairs * args.steps / dt
-    cfg = config_dict(1)
-    cfg["pairs_per_step"] = pairs
-    line = {"impl": "reference", "metric": "query-doc pairs scored/sec (ColBERT max-sim d=128)", "value": v,
-            "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": cfg,
+    per = wl.cpu_pairs() if hasattr(wl, "cpu_pairs") else (getattr(wl, "cpu_n", None) or wl.pairs)
+    v = per * args.steps / dt
+    cfg = wl.config(1)
+    cfg["pairs_per_step"] = per
+    cfg["reference_step"] = "each step = %d pairs of the workload (bounded CPU sample)" % per
+    line = {"impl": "reference", "metric": wl.metric, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"each step = full workload {N_QUERIES}x{DOCS_PER_QUERY} pairs on "
-                                       f"{torch.get_num_threads()} torch threads ({os.cpu_count()} logical cores)"},
+                             "sample": "each step = %d pairs on %d torch threads (%d logical cores)"
+                                       % (per, torch.get_num_threads(), os.cpu_count())},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -182,6 +469,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="colbert", choices=["colbert", "tk", "knrm", "tkl", "bert_dot"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: min(steps, 5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -195,7 +483,6 @@ def main():
         return
 
     import torch.distributed as dist
-    from matchmaker_b200 import interaction, sharding
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -204,16 +491,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    q, d, qm, dm = make_inputs(rank)
-    qm_b, dm_b = qm.bool(), dm.bool()
-    cq, cd, cqm, cdm = q.to(dev), d.to(dev), qm_b.to(dev), dm_b.to(dev)
-    doc_id_base = rank * N_QUERIES * DOCS_PER_QUERY
+    wl = make_workload(args.workload, rank, dev)
+    wl.to_device()
 
     def step():
-        s = interaction.maxsim(cq, cd, cqm, cdm, docs_per_query=DOCS_PER_QUERY, impl="tcgen05")
-        if world > 1:
-            return sharding.topk_all_gather_merge(s.view(N_QUERIES, DOCS_PER_QUERY), TOPK, doc_id_base)
-        return s
+        out = wl.kernel_step()
+        return wl.exchange(out) if world > 1 else out
 
     def sync_all():
         torch.cuda.synchronize()
@@ -236,10 +519,10 @@ def main():
     e0.record()
     for i in range(args.steps):
         kern_ev[i][0].record()
-        s = interaction.maxsim(cq, cd, cqm, cdm, docs_per_query=DOCS_PER_QUERY, impl="tcgen05")
+        out = wl.kernel_step()
         kern_ev[i][1].record()
         if world > 1:
-            sharding.topk_all_gather_merge(s.view(N_QUERIES, DOCS_PER_QUERY), TOPK, doc_id_base)
+            wl.exchange(out)
     e1.record()
     sync_all()
     t_val1 = time.perf_counter()
@@ -250,18 +533,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, kern_ms = t.tolist()
     ms_per_step = ms_total / args.steps
-    pairs_per_step = N_QUERIES * DOCS_PER_QUERY * world
+    pairs_per_step = wl.pairs * world
     value = pairs_per_step / (ms_per_step * 1e-3)
 
-    # ---- e2e: host-buffer C-ABI call, H2D + kernel + D2H inside the timed region ------------------
-    hq, hd, hqm, hdm = q.pin_memory(), d.pin_memory(), qm_b.pin_memory(), dm_b.pin_memory()
+    # ---- e2e: public API with HOST buffers, H2D + kernel + D2H inside the timed region -------------
+    h2d = wl.pin()
     e2e_steps = args.e2e_steps or min(args.steps, 5)
     for _ in range(2):
-        interaction.maxsim_host(hq, hd, hqm, hdm, docs_per_query=DOCS_PER_QUERY, device=dev)
+        wl.e2e_step()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = interaction.maxsim_host(hq, hd, hqm, hdm, docs_per_query=DOCS_PER_QUERY, device=dev)  # synchronous
+        out = wl.e2e_step()  # ends with a device->host read of the result
     torch.cuda.synchronize()
     t_e2e1 = time.perf_counter()
     clocks = sampler.stop([(t_val0, t_val1), (t0, t_e2e1)]) if rank == 0 else None
@@ -270,37 +553,37 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = te.item()
-    h2d = sum(x.numel() * x.element_size() for x in (hq, hd, hqm, hdm))
     d2h = out.numel() * out.element_size()
 
     if rank == 0:
-        peak, peak_src = _peaks()
-        alg_bytes = ALG_BYTES_PER_PAIR * N_QUERIES * DOCS_PER_QUERY
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        line = {
-            "metric": "query-doc pairs scored/sec (ColBERT max-sim d=128)", "value": value, "unit": "pairs/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": config_dict(world),
-            "clocks": clocks,
-            "e2e": {"value": pairs_per_step / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-                    "note": "mmb200_maxsim_fwd_host: pinned host q/d/masks -> chunked H2D overlapped with the "
-                            "kernel -> D2H scores; PCIe-bound"},
-            "gpu_launches": args.steps,
-            "roofline": {"bound": "hbm", "kernel": "maxsim_qm_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "algorithmic_bytes_per_pair": ALG_BYTES_PER_PAIR},
-        }
+        hbm_peak, peak_src = _peaks()
+        if wl.bound == "hbm":
+            achieved = wl.alg_bytes / (kern_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": wl.kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                    "algorithmic_bytes_per_launch": wl.alg_bytes, "algorithmic_bytes": wl.alg_note}
+        else:
+            tf_peak, tf_src = _tensor_peak()
+            achieved = wl.flops / (kern_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": wl.kernel, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tf_peak, "traffic": None, "peak_source": tf_src, "kernel_ms": kern_ms,
+                    "algorithmic_flops_per_launch": wl.flops, "algorithmic_flops": wl.alg_note}
+        line = {"metric": wl.metric, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(world),
+                "clocks": clocks,
+                "e2e": {"value": pairs_per_step / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "note": wl.e2e_note},
+                "gpu_launches": args.steps * (2 if args.workload in ("tkl", "bert_dot") else 1),
+                "roofline": roof}
         prof = os.path.join(ROOT, "profiles", "maxsim_traffic.json")
-        if os.path.isfile(prof):
+        if args.workload == "colbert" and os.path.isfile(prof):
             try:
                 line["roofline"]["traffic"] = json.load(open(prof))["dram_bytes_per_launch"]
             except Exception:
                 pass
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = time_cpu_baseline(q, d, qm, dm)
+            line["cpu_baseline"] = time_cpu(wl)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -196,6 +196,33 @@ MMB200_API int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
 MMB200_API int mmb200_tkl_top_hills(float* window_score, const float* chunk_scoring, int64_t* top_idx,
                                     float* top15, float* score, int64_t B, int32_t W, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Exact maximum-inner-product search with fused per-query top-k (BERT_DOT dense retrieval scoring)
+ *
+ * Replaces: FaissIdIndexer / FaissBaseIndexer.search   matchmaker/retrieval/faiss_indices.py:27,34,49-74
+ *           (faiss.IndexIDMap(IndexFlatIP), GPU-sharded, useFloat16), called from
+ *           matchmaker/dense_retrieval.py:328 (index) and :391 (search).
+ *
+ * queries  [nq, dim], passages [n_pass, dim]: fp16 or bf16 (`dtype`), dim % 64 == 0, row-major,
+ *          resident on the current device (one shard per GPU); fp32 accumulate on the tensor cores.
+ * ids      [n_pass] int64 user ids (add_with_ids) or NULL: id = id_base + row.
+ * out_scores [nq, k] f32 descending; out_ids [nq, k] int64; ties ordered by id ascending (faiss leaves
+ *          tie order unspecified); when n_pass < k the tail is (-3.4028235e38, -1) as in faiss.
+ * workspace: device scratch of at least mmb200_flat_ip_workspace_bytes(nq, n_pass, k) bytes.
+ * 1 <= k <= 256.
+ * ------------------------------------------------------------------------------------------ */
+MMB200_API int64_t mmb200_flat_ip_workspace_bytes(int64_t nq, int64_t n_pass, int32_t k);
+MMB200_API int mmb200_flat_ip_topk(const void* queries, const void* passages, const int64_t* ids,
+                                   float* out_scores, int64_t* out_ids, void* workspace,
+                                   int64_t workspace_bytes, int64_t nq, int64_t n_pass, int32_t dim, int32_t k,
+                                   int32_t dtype, int64_t id_base, void* stream);
+
+/* Merge candidate lists: cand_scores / cand_ids [nq, n_candidates] (entries with id < 0 or score -inf
+ * are ignored) -> the k best per query under (score desc, id asc).  Used after the NCCL all-gather of
+ * per-rank top-k lists (the reference merges faiss IndexShards results on the host). */
+MMB200_API int mmb200_topk_merge(const float* cand_scores, const int64_t* cand_ids, float* out_scores,
+                                 int64_t* out_ids, int64_t nq, int32_t n_candidates, int32_t k, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -311,3 +311,47 @@ def tkl_top_hills(window_score: torch.Tensor, chunk_scoring: torch.Tensor):
                                       _ptr(score), B, W, _stream(dev))
     _lib.check(rc, "mmb200_tkl_top_hills")
     return score, ws, top_idx, top15
+
+
+def flat_ip_topk(queries: torch.Tensor, passages: torch.Tensor, k: int, ids: Optional[torch.Tensor] = None,
+                 id_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact inner-product top-k of every query against a resident passage shard (faiss IndexFlatIP
+    semantics, faiss_indices.py:34).  queries [nq,dim], passages [n,dim] fp16/bf16; returns
+    (scores [nq,k] f32 descending, ids [nq,k] int64); ties by id ascending."""
+    dev = _require_cuda(queries, passages, ids)
+    if passages.dtype not in (torch.float16, torch.bfloat16):
+        raise _lib.MatchmakerB200Error("flat_ip_topk: passage storage must be fp16 or bf16")
+    queries = queries.to(passages.dtype).contiguous()
+    passages = passages.contiguous()
+    nq, dim = queries.shape
+    n = passages.shape[0]
+    if ids is not None:
+        ids = ids.to(torch.int64).contiguous()
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        wsb = lib.mmb200_flat_ip_workspace_bytes(nq, n, k)
+        if wsb <= 0:
+            raise _lib.MatchmakerB200Error(f"flat_ip_topk: unsupported sizes nq={nq} n={n} k={k} (1 <= k <= 256): "
+                                           + _lib.last_error())
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        rc = lib.mmb200_flat_ip_topk(_ptr(queries), _ptr(passages), _ptr(ids), _ptr(out_s), _ptr(out_i), _ptr(ws), wsb,
+                                     nq, n, dim, k, _DTYPES[passages.dtype], id_base, _stream(dev))
+    _lib.check(rc, "mmb200_flat_ip_topk")
+    return out_s, out_i
+
+
+def topk_merge(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-query merge of candidate lists [nq, L] -> top-k under (score desc, id asc)."""
+    dev = _require_cuda(cand_scores, cand_ids)
+    cand_scores = cand_scores.to(torch.float32).contiguous()
+    cand_ids = cand_ids.to(torch.int64).contiguous()
+    nq, L = cand_scores.shape
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.mmb200_topk_merge(_ptr(cand_scores), _ptr(cand_ids), _ptr(out_s), _ptr(out_i), nq, L, k, _stream(dev))
+    _lib.check(rc, "mmb200_topk_merge")
+    return out_s, out_i

@@ -15,6 +15,25 @@ from .. import interaction
 from .tk import sinusoid_position_features
 
 
+def chunk_documents(document_embeddings: torch.Tensor, document_mask: torch.Tensor, chunk_size: int = 40,
+                    overlap: int = 5):
+    """Pad (5 left, >= 10 right), unfold into extended chunks of 50 at stride 40, and mark the chunks whose 40
+    centre positions hold at least one real token (sigir20_tkl.py:142-162).  Returns (chunks [B*C,50,D],
+    chunk masks [B*C,50], packed [B*C] bool, C)."""
+    ext = chunk_size + 2 * overlap
+    ld = document_mask.shape[1]
+    needed = ext - ((ld - overlap) % chunk_size) if ld > overlap else ext - overlap - ld
+    emb = nn.functional.pad(document_embeddings, (0, 0, overlap, needed))
+    msk = nn.functional.pad(document_mask, (overlap, needed))
+    chunks = emb.unfold(1, ext, chunk_size).transpose(-1, -2)
+    cmask = msk.unfold(1, ext, chunk_size)
+    pieces = chunks.shape[1]
+    chunks2 = chunks.reshape(-1, ext, emb.shape[-1])
+    cmask2 = cmask.reshape(-1, ext)
+    packed = cmask2[:, overlap:-overlap].sum(-1) != 0
+    return chunks2, cmask2, packed, pieces
+
+
 class TKL_sigir20(nn.Module):
     """forward(query_embeddings, document_embeddings, query_pad_oov_mask, document_pad_oov_mask,
     output_secondary_output=False) -> score [B] (sigir20_tkl.py:128-294).  Parameter names / shapes match the
@@ -82,20 +101,7 @@ class TKL_sigir20(nn.Module):
 
     # -- chunking (sigir20_tkl.py:142-162) -----------------------------------------------------
     def chunk_documents(self, document_embeddings: torch.Tensor, document_mask: torch.Tensor):
-        ld = document_mask.shape[1]
-        if ld > self.overlap:
-            needed = self.extended_chunk_size - ((ld - self.overlap) % self.chunk_size)
-        else:
-            needed = self.extended_chunk_size - self.overlap - ld
-        emb = nn.functional.pad(document_embeddings, (0, 0, self.overlap, needed))
-        msk = nn.functional.pad(document_mask, (self.overlap, needed))
-        chunks = emb.unfold(1, self.extended_chunk_size, self.chunk_size).transpose(-1, -2)
-        cmask = msk.unfold(1, self.extended_chunk_size, self.chunk_size)
-        pieces = chunks.shape[1]
-        chunks2 = chunks.reshape(-1, self.extended_chunk_size, emb.shape[-1])
-        cmask2 = cmask.reshape(-1, self.extended_chunk_size)
-        packed = cmask2[:, self.overlap:-self.overlap].sum(-1) != 0
-        return chunks2, cmask2, packed, pieces
+        return chunk_documents(document_embeddings, document_mask, self.chunk_size, self.overlap)
 
     def _saturation_params(self):
         if self.saturation_type == "embedding":

@@ -49,6 +49,9 @@ def all_gather_merge(local_scores: torch.Tensor, local_ids: torch.Tensor, k: int
     dist.all_gather_into_tensor(gi, local_ids.contiguous(), group=group)
     cs = gs.view(world, nq, kl).permute(1, 0, 2).reshape(nq, world * kl)
     ci = gi.view(world, nq, kl).permute(1, 0, 2).reshape(nq, world * kl)
+    if cs.is_cuda:  # k-way merge on the GPU kernel (mmb200_topk_merge); torch ops only for the gloo/CPU tests
+        from . import interaction
+        return interaction.topk_merge(cs, ci, min(k, world * kl))
     return rank_topk(cs, ci, k)
 
 
@@ -58,5 +61,9 @@ def topk_all_gather_merge(local_scores: torch.Tensor, k: int, id_base: int,
     shard has global id ``id_base + j``."""
     nq, n = local_scores.shape
     ids = torch.arange(id_base, id_base + n, device=local_scores.device, dtype=torch.int64)
-    ls, li = rank_topk(local_scores, ids, k)
+    if local_scores.is_cuda:
+        from . import interaction
+        ls, li = interaction.topk_merge(local_scores, ids.unsqueeze(0).expand(nq, -1), min(k, n))
+    else:
+        ls, li = rank_topk(local_scores, ids, k)
     return all_gather_merge(ls, li, k, group)
