@@ -59,6 +59,8 @@ extern "C" {
 #define MMB200_IMPL_SIMT 1    /* CUDA-core kernel, any shape/dtype */
 #define MMB200_IMPL_TCGEN05 2 /* TMA + tcgen05 tensor-core kernel (fails if shape unsupported) */
 #define MMB200_IMPL_TCGEN05_DOCM 3 /* max-sim only: the first-generation "documents on M" tcgen05 kernel */
+#define MMB200_IMPL_TCGEN05_RAGGED 4 /* max-sim only: tcgen05 kernel that fetches each document only up to its
+                                        last unmasked row (padding rows never leave HBM / host memory) */
 
 MMB200_API int mmb200_version(void);
 MMB200_API const char* mmb200_last_error(void);
@@ -109,7 +111,11 @@ MMB200_API int mmb200_maxsim_bwd(const void* q, const void* d, const float* grad
 /* Host-buffer variant (the end-to-end call): all pointers are HOST pointers (pinned memory
  * gives full PCIe bandwidth, pageable works).  Documents are streamed to the device in chunks
  * on internal streams, overlapped with the kernel; scores are copied back before returning.
- * Synchronous.  Same semantics as mmb200_maxsim_fwd with pair_q = pair_d = NULL. */
+ * Synchronous.  Same semantics as mmb200_maxsim_fwd with pair_q = pair_d = NULL.
+ * When d_host is pinned (device-mapped) memory and the shape fits the queries-on-M kernel, the
+ * documents are not staged at all: the kernel's TMA reads them directly over PCIe, 16 rows at a time, and
+ * only up to each document's last unmasked row.  chunk_pairs: 0 = default slab size, -1 = force the
+ * staged (slab) pipeline. */
 MMB200_API int mmb200_maxsim_fwd_host(const void* q_host, const void* d_host, const void* q_mask_host,
                            const void* d_mask_host, float* out_host, int64_t n_q, int64_t n_d,
                            int32_t docs_per_query, int32_t Lq, int32_t Ld, int32_t dim, int32_t dtype,

@@ -16,7 +16,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
 F16, BF16, F32 = 0, 1, 2
 MASK_NONE, MASK_U8, MASK_I32, MASK_I64, MASK_F32 = 0, 1, 2, 3, 4
-IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_TCGEN05_DOCM = 0, 1, 2, 3
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_TCGEN05_DOCM, IMPL_TCGEN05_RAGGED = 0, 1, 2, 3, 4
 
 _c = ctypes
 _vp, _i32, _i64, _f32 = _c.c_void_p, _c.c_int32, _c.c_int64, _c.c_float

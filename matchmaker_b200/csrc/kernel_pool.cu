@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "host_util.cuh"
+#include "kernel_pool.cuh"
 #include "masks.cuh"
 
 namespace mmb {
@@ -29,32 +30,6 @@ __host__ __device__ inline int kp_row_stride(int D) {
   if (((dp >> 2) & 1) == 0) dp += 4;  // (dp/4) odd -> 8 consecutive rows hit 8 distinct 16-B bank groups
   return dp;
 }
-
-struct KpParams {
-  const float* q;
-  const float* d;
-  const void* q_mask;
-  const void* d_mask;
-  const float* mu;
-  const float* sigma;
-  const float* alpha;
-  const float* weight;
-  int64_t B;
-  int32_t Lq, Ld, D, K, mask_dtype;
-  float log_scale;
-  // forward outputs
-  float* score;
-  float* per_kernel;
-  float* per_kernel_query;
-  float* cosine;
-  // backward
-  const float* S;
-  const float* grad_score;
-  float* grad_q;
-  float* grad_d;
-  float* ws_weight;  // [B,K]
-  float* ws_alpha;   // [B,K]
-};
 
 // Load `nrows` rows (row r of the tile = global row row0 + r, valid while < L) of a [L, D] matrix,
 // L2-normalise them (x / (|x| + 1e-13)) and store into smem with stride dp.  Rows past L become zeros.
@@ -449,7 +424,6 @@ __global__ void kp_reduce_batch(const float* __restrict__ ws_w, const float* __r
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
-int kernel_pool_fwd_tc(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, bool* handled);  // kernel_pool_tc.cu
 
 static int kp_validate(const KpParams& P) {
   MMB_REQUIRE(P.q && P.d && P.mu && P.sigma && P.weight, "null pointer");

