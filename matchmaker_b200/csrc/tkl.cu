@@ -27,6 +27,7 @@ constexpr int kWindow = 30;     // :56
 constexpr int kPairsPerChunk = kChunk / 2;
 constexpr int kWinPairs = kWindow / 2;  // 15
 constexpr int kRing = 2 * kPairsPerChunk;  // pairs kept: previous + current chunk
+constexpr int kZStride = kRing + 1;        // odd strides: the window phase walks query rows across lanes
 constexpr int kMaxLq = 40;
 constexpr float kTiny = 1e-13f;
 constexpr float kClamp = 1e-10f;
@@ -142,9 +143,10 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
   float* qs = sm;                                   // [40][dp]  normalised query rows
   float* ds = qs + (size_t)kMaxLq * dp;             // [40][dp]  normalised chunk rows
   float* cs = ds + (size_t)kChunk * dp;             // [40][41]
+  constexpr int UST = kRing * KB + 1;               // row stride of U (odd -> no bank conflicts across query rows)
   float* U = cs + kMaxLq * 41;                      // [40 i][kRing][KB] pair sums of activations
-  float* Z = U + (size_t)kMaxLq * kRing * KB;       // [40 i][kRing] non-zero position counts per pair
-  float* red = Z + kMaxLq * kRing;                  // [40] sat_emb_reduce1(q_i)
+  float* Z = U + (size_t)kMaxLq * UST;              // [40 i][kRing] non-zero position counts per pair
+  float* red = Z + kMaxLq * kZStride;               // [40] sat_emb_reduce1(q_i)
   float* qm_s = red + kMaxLq;                       // [40]
   float* dm_s = qm_s + kMaxLq;                      // [40]
   float* mu_s = dm_s + kChunk;                      // [KB]
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
       for (int e = t; e < kMaxLq * kPairsPerChunk; e += kThreads) {
         const int i = e / kPairsPerChunk, ul = e % kPairsPerChunk;
         const int slot = (c * kPairsPerChunk + ul) % kRing;
-        float* u = U + ((size_t)i * kRing + slot) * KB;
+        float* u = U + (size_t)i * UST + slot * KB;
         float nz = 0.f;
         if (pk_idx >= 0 && i < Lq) {
           const int p0 = 2 * ul, p1 = p0 + 1;
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
 #pragma unroll
           for (int k = 0; k < KB; ++k) u[k] = 0.f;
         }
-        Z[i * kRing + slot] = nz;
+        Z[i * kZStride + slot] = nz;
       }
       __syncthreads();
       if (c < c_first) continue;  // halo chunk: nothing to finish
@@ -228,10 +230,10 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
         float len = 0.f;
         for (int u = 0; u < kWinPairs; ++u) {
           const int slot = (w + u) % kRing;
-          const float* up = U + ((size_t)i * kRing + slot) * KB;
+          const float* up = U + (size_t)i * UST + slot * KB;
 #pragma unroll
           for (int k = 0; k < KB; ++k) S[k] += up[k];
-          len += Z[i * kRing + slot];
+          len += Z[i * kZStride + slot];
         }
         const float gate = (i < Lq && qm_s[i] != 0.f && len > 0.f) ? 1.f : 0.f;  // :248
         float* Tp = T + ((size_t)wl * kMaxLq + i) * KB;
@@ -366,7 +368,7 @@ extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
   P.segs = (C + P.chunks_per_seg - 1) / P.chunks_per_seg;
   const int KB = K <= 12 ? 12 : 16;
   const int dp = tkl_row_stride(D);
-  const size_t need = ((size_t)2 * kMaxLq * dp + kMaxLq * 41 + (size_t)kMaxLq * kRing * KB + kMaxLq * kRing + 3 * kMaxLq +
+  const size_t need = ((size_t)2 * kMaxLq * dp + kMaxLq * 41 + (size_t)kMaxLq * (kRing * KB + 1) + kMaxLq * kZStride + 3 * kMaxLq +
                        4 * KB + 16 + 20 * KB + (size_t)20 * kMaxLq * KB) * sizeof(float);
   if (need > (size_t)dev.max_smem_optin) {
     set_error("TKL kernel: embedding dim / kernel count too large for the shared-memory plan (D=300 fits with K <= 12)");

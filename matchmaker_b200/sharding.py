@@ -43,12 +43,14 @@ def all_gather_merge(local_scores: torch.Tensor, local_ids: torch.Tensor, k: int
         return rank_topk(local_scores, local_ids, k)
     world = dist.get_world_size(group)
     nq, kl = local_scores.shape
-    gs = torch.empty((world * nq, kl), dtype=local_scores.dtype, device=local_scores.device)
-    gi = torch.empty((world * nq, kl), dtype=local_ids.dtype, device=local_ids.device)
-    dist.all_gather_into_tensor(gs, local_scores.contiguous(), group=group)  # rank-major concatenation
-    dist.all_gather_into_tensor(gi, local_ids.contiguous(), group=group)
-    cs = gs.view(world, nq, kl).permute(1, 0, 2).reshape(nq, world * kl)
-    ci = gi.view(world, nq, kl).permute(1, 0, 2).reshape(nq, world * kl)
+    # ONE collective: (score bits, id) packed as int64 pairs -> [world * nq, kl, 2]
+    packed = torch.stack([local_scores.contiguous().view(torch.int32).to(torch.int64), local_ids.contiguous()], dim=-1)
+    gathered = torch.empty((world * nq, kl, 2), dtype=torch.int64, device=packed.device)
+    dist.all_gather_into_tensor(gathered, packed, group=group)  # rank-major concatenation
+    gs = gathered[..., 0].to(torch.int32).view(torch.float32)
+    gi = gathered[..., 1]
+    cs = gs.reshape(world, nq, kl).permute(1, 0, 2).reshape(nq, world * kl)
+    ci = gi.reshape(world, nq, kl).permute(1, 0, 2).reshape(nq, world * kl)
     if cs.is_cuda:  # k-way merge on the GPU kernel (mmb200_topk_merge); torch ops only for the gloo/CPU tests
         from . import interaction
         return interaction.topk_merge(cs, ci, min(k, world * kl))

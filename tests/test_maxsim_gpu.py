@@ -199,3 +199,30 @@ def test_invalid_arguments_raise():
         interaction.maxsim(q, d.float())
     with pytest.raises(_lib.MatchmakerB200Error):
         interaction.maxsim(q.float(), d.float(), docs_per_query=3, impl="tcgen05")  # fp32 has no tcgen05 path
+
+
+def test_colbert_token_index_rerank():
+    """Retrieval aggregation over a resident token store (the working version of dense_retrieval.py:398-412)."""
+    import numpy as np
+    from matchmaker_b200.retrieval import ColBERTTokenIndex
+    g = torch.Generator().manual_seed(31)
+    n, dim, Lmax = 300, 128, 180
+    lens = torch.randint(5, Lmax + 1, (n,), generator=g)
+    mats = [torch.nn.functional.normalize(torch.randn(int(l), dim, generator=g), dim=-1).half().numpy() for l in lens]
+    ext_ids = np.arange(n, dtype=np.int64) * 7 + 3
+    idx = ColBERTTokenIndex(dim, Lmax)
+    idx.index(ext_ids, mats)
+    q = torch.nn.functional.normalize(torch.randn(4, 32, dim, generator=g), dim=-1).half()
+    cand = torch.stack([torch.randperm(n, generator=g)[:50] for _ in range(4)])
+    cand[2, 40:] = -1
+    s, ids = idx.rerank(q, None, cand, top_n=10)
+    for qi in range(4):
+        ref = []
+        for c in cand[qi].tolist():
+            if c < 0:
+                continue
+            d = torch.from_numpy(mats[c]).float().unsqueeze(0)
+            ref.append((O.maxsim_pairs(q[qi:qi + 1].float(), d, None, None).item(), int(ext_ids[c])))
+        ref.sort(key=lambda t: (-t[0], t[1]))
+        assert ids[qi].cpu().tolist() == [r[1] for r in ref[:10]]
+        assert_close_rel(s[qi].cpu(), torch.tensor([r[0] for r in ref[:10]]), what="rerank scores")
