@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "host_util.cuh"
 #include "ptx.cuh"
@@ -176,7 +177,9 @@ template <int EPL>
 __global__ void __launch_bounds__(kThreads, 1)
 flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_p, FipParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-B alignment for SWIZZLE_128B tiles, derived by pointer arithmetic on the __shared__ array so the
+  // compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   FipShared* S = reinterpret_cast<FipShared*>(smem + (size_t)kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = P.dim / 64;
@@ -405,16 +408,25 @@ Plan make_plan(int64_t nq, int64_t n_pass, int k, int sm_count) {
   pl.kpad = (k + 31) / 32 * 32;
   pl.epl = k <= 128 ? 16 : 32;
   pl.cap = 32 * pl.epl;
-  // number of passage ranges: maximise SM fill of the item grid, prefer fewer ranges on ties
+  // number of passage ranges: every range restarts its threshold at -inf and pays ~log(range/k) list
+  // compactions per query, so take the SMALLEST count whose item grid fills the SMs to >= 88 % (or the best
+  // fill available).  MMB200_FLATIP_RANGES overrides it for experiments.
   int best_r = 1;
   double best_eff = -1.0;
   const int max_r = std::max(1, std::min(kMaxRanges, pl.n_tiles));
+  double effs[kMaxRanges + 1];
   for (int r = 1; r <= max_r; ++r) {
     const int64_t items = (int64_t)pl.n_qblocks * r;
     const int64_t g = std::min<int64_t>(sm_count, items);
     const int64_t waves = (items + g - 1) / g;
-    const double eff = (double)items / (double)(waves * sm_count);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best_r = r; }
+    effs[r] = (double)items / (double)(waves * sm_count);
+    if (effs[r] > best_eff + 1e-9) { best_eff = effs[r]; best_r = r; }
+  }
+  for (int r = 1; r <= max_r; ++r)
+    if (effs[r] >= 0.88 || effs[r] >= best_eff - 1e-9) { best_r = r; break; }
+  if (const char* env = getenv("MMB200_FLATIP_RANGES")) {
+    const int r = atoi(env);
+    if (r >= 1 && r <= max_r) best_r = r;
   }
   pl.tiles_per_range = (pl.n_tiles + best_r - 1) / best_r;
   pl.n_ranges = (pl.n_tiles + pl.tiles_per_range - 1) / pl.tiles_per_range;

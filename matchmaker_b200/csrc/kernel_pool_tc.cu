@@ -37,7 +37,7 @@ namespace mmb {
 namespace {
 
 constexpr int kThreads = 480;
-constexpr int kStages = 3;
+constexpr int kMaxStages = 4;
 constexpr int kAcc = 4;
 constexpr int kDxBytes = 128 * 128;   // [128 rows][32 fp32]
 constexpr int kQ64Bytes = 64 * 128;   // rows 0-31 Q hi, rows 32-63 Q lo
@@ -49,9 +49,9 @@ constexpr float kTinyNorm = 1e-13f;
 constexpr float kClampMin = 1e-10f;
 
 struct KpShared {
-  uint64_t tma_full[kStages];
-  uint64_t conv_done[kStages];
-  uint64_t empty[kStages];
+  uint64_t tma_full[kMaxStages];
+  uint64_t conv_done[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t accfull[kAcc];
   uint64_t accempty[kAcc];
   uint32_t tmem_base;
@@ -71,9 +71,12 @@ __device__ __forceinline__ float ex2f(float x) {
 
 template <int KB>
 __global__ void __launch_bounds__(kThreads, 1)
-kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, KpParams P) {
+kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, KpParams P,
+                      int kStages) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-B alignment for SWIZZLE_128B tiles, derived by pointer arithmetic on the __shared__ array so the
+  // compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;
   float* cs = reinterpret_cast<float*>(smem + kStages * kStageBytes);          // [2][128][32] cosine tiles
   float* spart = cs + 2 * 128 * 32;                                            // [8][KB][32]
@@ -166,7 +169,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint32_t phase = 0;
     for (int64_t p = p_begin; p < p_end; ++p)
       for (int t = 0; t < tiles; ++t) {
-        float ss = 0.f;
+        float4 ss4 = make_float4(0.f, 0.f, 0.f, 0.f);  // four partial sums: shorter rounding chains for |x|^2
         for (int ck = 0; ck < nch; ++ck) {
           mbar_wait(&S->tma_full[stage], phase);
           uint8_t* st = stages + (size_t)stage * kStageBytes;
@@ -176,7 +179,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           for (int c = 0; c < 8; ++c) {
             const int off = ((c ^ sw) << 4);
             float4 x = *reinterpret_cast<float4*>(xrow + off);
-            ss = fmaf(x.x, x.x, ss); ss = fmaf(x.y, x.y, ss); ss = fmaf(x.z, x.z, ss); ss = fmaf(x.w, x.w, ss);
+            ss4.x = fmaf(x.x, x.x, ss4.x); ss4.y = fmaf(x.y, x.y, ss4.y); ss4.z = fmaf(x.z, x.z, ss4.z); ss4.w = fmaf(x.w, x.w, ss4.w);
             float4 hi, lo;
             hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); lo.x = x.x - hi.x;
             hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); lo.y = x.y - hi.y;
@@ -186,7 +189,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             *reinterpret_cast<float4*>(lrow + off) = lo;
           }
           if (ck == nch - 1) {
-            const float rs = 1.0f / (sqrtf(ss) + kTinyNorm);
+            const float rs = 1.0f / (sqrtf((ss4.x + ss4.y) + (ss4.z + ss4.w)) + kTinyNorm);
             if (is_q) S->rs_q[acc][row] = rs; else S->rs_d[acc][row] = rs;
           }
           fence_proxy_async_smem();
@@ -305,14 +308,16 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
 template <int KB>
 int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& td) {
-  const size_t smem = (size_t)kStages * kStageBytes + (size_t)(2 * 128 * 32 + 9 * KB * 32) * sizeof(float) + sizeof(KpShared) + 1024;
-  if (smem > (size_t)dev.max_smem_optin) {
+  const size_t fixed = (size_t)(2 * 128 * 32 + 9 * KB * 32) * sizeof(float) + sizeof(KpShared) + 1024;
+  const int kStages = std::min<int>(kMaxStages, (int)(((size_t)dev.max_smem_optin - fixed) / kStageBytes));
+  const size_t smem = (size_t)kStages * kStageBytes + fixed;
+  if (kStages < 2 || smem > (size_t)dev.max_smem_optin) {
     set_error("kernel_pool tcgen05: shared-memory plan does not fit");
     return MMB200_ERR_UNSUPPORTED;
   }
   MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(dev.sm_count, P.B);
-  kernel_pool_tc_kernel<KB><<<grid, kThreads, smem, stream>>>(tq, td, P);
+  kernel_pool_tc_kernel<KB><<<grid, kThreads, smem, stream>>>(tq, td, P, kStages);
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;
 }

@@ -221,7 +221,9 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                  MaxsimParams P, TcLaunch L) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-B alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-B alignment for SWIZZLE_128B tiles, derived by pointer arithmetic on the __shared__ array so the
+  // compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int kStageBytes = KBS * kKBlockBytes;
   uint8_t* stage_base = smem;
   uint8_t* q_base = smem + (size_t)L.stages * kStageBytes;

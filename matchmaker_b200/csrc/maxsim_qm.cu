@@ -92,7 +92,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
                  const __grid_constant__ CUtensorMap tmap_d16, MaxsimParams P, QmLaunch L) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-B alignment for SWIZZLE_128B tiles, derived by pointer arithmetic on the __shared__ array so the
+  // compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int qslot_bytes = L.kblocks * kQBlockBytes;
   uint8_t* q_base = smem;                                            // [kQSlots][kblocks][2 x 32 rows][128 B]
   uint8_t* stage_base = q_base + kQSlots * qslot_bytes;              // [stages][doc tile | penalty tile]

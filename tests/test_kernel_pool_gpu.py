@@ -16,6 +16,16 @@ def _c(*ts):
     return [None if t is None else t.to(DEV) for t in ts]
 
 
+def assert_score_close(actual, expected, per_kernel, weight, rel=1e-3, what=""):
+    """score = sum_k w_k * P_k is a signed sum whose terms cancel (|w_k P_k| ~ 1..30 while |score| can be ~0): the
+    1e-3 bar is applied relative to max(|score|, 1e-2 * sum_k |w_k P_k|), i.e. 1e-5 of the magnitude actually summed."""
+    a, b = actual.detach().double().cpu(), expected.detach().double().cpu()
+    scale = (per_kernel.detach().double().cpu().abs() * weight.detach().double().cpu().abs().view(1, -1)).sum(1)
+    tol = rel * torch.maximum(b.abs(), 1e-2 * scale)
+    err = (a - b).abs()
+    assert (err <= tol).all(), f"{what}: {int((err > tol).sum())}/{err.numel()} off, worst {err.max().item():.3e}"
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("tag", ["small", "cfg1"])
 def test_golden_knrm(tag, impl):
@@ -164,9 +174,10 @@ def test_baseline_cfg2_size_properties():
                                    alpha=alpha.to(DEV))
     assert torch.equal(outp["score"], out["score"][perm])
     simt = interaction.kernel_pool(*args, alpha=alpha.to(DEV), impl="simt")
-    assert_close_rel(out["score"], simt["score"], what="auto vs simt")
-    ref, _ = O.kernel_pool_tk(q[:16], d[:16], qm[:16], dm[:16], mu, sg, alpha, w)
-    assert_close_rel(out["score"][:16], ref, what="oracle slice")
+    assert_score_close(out["score"], simt["score"], out["per_kernel"], w, what="auto vs simt")
+    ref, sec = O.kernel_pool_tk(q[:16], d[:16], qm[:16], dm[:16], mu, sg, alpha, w)
+    assert_score_close(out["score"][:16], ref, sec["per_kernel"], w, what="oracle slice")
+    assert_close_rel(out["per_kernel"][:16], sec["per_kernel"], what="per_kernel slice")
 
 
 @pytest.mark.parametrize("shape", [(7, 30, 180, 300, "knrm11"), (5, 30, 200, 300, "tk21"), (3, 32, 77, 64, "tk11"),
@@ -190,10 +201,14 @@ def test_tcgen05_forward_vs_oracle(shape):
     assert_close_rel(out["score"], ref, what=f"score {shape}")
     assert_close_rel(out["per_kernel"], sec["per_kernel"], what="per_kernel")
     valid = qm.bool()
-    assert_close_rel(out["per_kernel_query"].cpu()[valid], sec["per_kernel_query"][valid], what="S (valid query rows)")
+    # S is an intermediate (saved for backward), not a reference output.  For KNRM's exact-match kernel
+    # (sigma = 1e-4) a cosine error of 4e-6 -- fp32 accumulation-order noise of the tensor-core contraction against
+    # the separately summed norms -- already moves exp(-(c-1)^2 / 2e-8) by 1e-3, so S gets 5e-3 here while every
+    # reference OUTPUT (score, per_kernel) is held to 1e-3.
+    assert_close_rel(out["per_kernel_query"].cpu()[valid], sec["per_kernel_query"][valid], rel=5e-3, what="S (valid query rows)")
     simt = interaction.kernel_pool(*_c(q, d, qm, dm, mu, sg, w), alpha=None if alpha is None else alpha.to(DEV),
                                    log_scale=ls, impl="simt")
-    assert_close_rel(out["score"], simt["score"], what="tcgen05 vs FFMA kernel")
+    assert_score_close(out["score"], simt["score"], sec["per_kernel"], w, what="tcgen05 vs FFMA kernel")
 
 
 def test_tcgen05_golden():
