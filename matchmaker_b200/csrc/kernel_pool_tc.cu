@@ -12,9 +12,10 @@
 //
 // Per CTA (persistent, one per SM, 480 threads):
 //   warp 0      TMA producer: fp32 K-chunks [128 doc rows x 32] (16 KB) + [32 query rows x 32] (4 KB),
-//               SWIZZLE_128B, 3 stages; rows >= Ld / columns >= D are zero-filled by the TMA unit
-//   warps 2-6   convert (one thread per row): hi in place, lo to a second tile, running sum of squares
-//               for the L2 norms (the normalisation is applied to the accumulator, not to the operands)
+//               SWIZZLE_128B, into a RAW ring (4 slots of 20 KB); rows >= Ld / columns >= D zero-filled by TMA
+//   warps 2-6   convert (one thread per row): raw slot -> registers -> hi / lo written to a 2-slot OPERAND ring
+//               (the raw slot is released as soon as the values are stored, not when the MMA retires), running sum of
+//               squares for the L2 norms (the normalisation is applied to the accumulator, not the operands)
 //   warp 1      tcgen05.mma kind::tf32 issuer, 4 accumulator slots of 64 TMEM columns
 //   warps 7-14  epilogue.  Phase A: tcgen05.ld, add the two halves, scale by 1/(|q|+eps) 1/(|d|+eps), write
 //               the cosine tile to shared memory TRANSPOSED-friendly (16-byte chunks XOR-swizzled) with
@@ -37,11 +38,14 @@ namespace mmb {
 namespace {
 
 constexpr int kThreads = 480;
-constexpr int kMaxStages = 4;
+constexpr int kMaxRaw = 8;            // raw ring (TMA targets): 20 KB per slot
+constexpr int kOps = 2;               // operand ring (what the MMA reads): 40 KB per slot
 constexpr int kAcc = 4;
 constexpr int kDxBytes = 128 * 128;   // [128 rows][32 fp32]
+constexpr int kQxBytes = 32 * 128;    // [32 query rows][32 fp32]
+constexpr int kRawBytes = kDxBytes + kQxBytes;          // 20 KB
 constexpr int kQ64Bytes = 64 * 128;   // rows 0-31 Q hi, rows 32-63 Q lo
-constexpr int kStageBytes = 2 * kDxBytes + kQ64Bytes;  // 40 KB
+constexpr int kOpBytes = 2 * kDxBytes + kQ64Bytes;      // 40 KB: Dhi | Dlo | [Qhi;Qlo]
 constexpr int kConvThreads = 160;
 constexpr int kEpiThreads = 256;
 constexpr float kSentinel = 1.0e4f;   // "cosine" of a masked row: every kernel underflows to exactly 0
@@ -49,9 +53,10 @@ constexpr float kTinyNorm = 1e-13f;
 constexpr float kClampMin = 1e-10f;
 
 struct KpShared {
-  uint64_t tma_full[kMaxStages];
-  uint64_t conv_done[kMaxStages];
-  uint64_t empty[kMaxStages];
+  uint64_t raw_full[kMaxRaw];    // TMA -> convert
+  uint64_t raw_empty[kMaxRaw];   // convert (160 arrivals) -> TMA
+  uint64_t op_full[kOps];        // convert (160 arrivals) -> MMA
+  uint64_t op_empty[kOps];       // tcgen05.commit -> convert
   uint64_t accfull[kAcc];
   uint64_t accempty[kAcc];
   uint32_t tmem_base;
@@ -72,13 +77,14 @@ __device__ __forceinline__ float ex2f(float x) {
 template <int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, KpParams P,
-                      int kStages) {
+                      int n_raw) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment for SWIZZLE_128B tiles, derived by pointer arithmetic on the __shared__ array so the
   // compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* stages = smem;
-  float* cs = reinterpret_cast<float*>(smem + kStages * kStageBytes);          // [2][128][32] cosine tiles
+  uint8_t* ops = smem;                                                          // [kOps][Dhi | Dlo | Q64]
+  uint8_t* raws = smem + kOps * kOpBytes;                                       // [n_raw][Dx | Qx]
+  float* cs = reinterpret_cast<float*>(raws + (size_t)n_raw * kRawBytes);       // [2][128][32] cosine tiles
   float* spart = cs + 2 * 128 * 32;                                            // [8][KB][32]
   float* lsm = spart + 8 * KB * 32;                                            // [KB][32]
   KpShared* S = reinterpret_cast<KpShared*>(lsm + KB * 32);
@@ -93,11 +99,8 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmap_q);
     prefetch_tensormap(&tmap_d);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&S->tma_full[s], 1);
-      mbar_init(&S->conv_done[s], kConvThreads);
-      mbar_init(&S->empty[s], 1);
-    }
+    for (int s = 0; s < n_raw; ++s) { mbar_init(&S->raw_full[s], 1); mbar_init(&S->raw_empty[s], kConvThreads); }
+    for (int s = 0; s < kOps; ++s) { mbar_init(&S->op_full[s], kConvThreads); mbar_init(&S->op_empty[s], 1); }
     for (int s = 0; s < kAcc; ++s) { mbar_init(&S->accfull[s], 1); mbar_init(&S->accempty[s], 8); }
     fence_barrier_init();
   }
@@ -123,12 +126,12 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       for (int64_t p = p_begin; p < p_end; ++p)
         for (int t = 0; t < tiles; ++t)
           for (int ck = 0; ck < nch; ++ck) {
-            mbar_wait(&S->empty[stage], phase ^ 1u);
-            uint8_t* st = stages + (size_t)stage * kStageBytes;
-            mbar_arrive_expect_tx(&S->tma_full[stage], (uint32_t)(kDxBytes + 32 * 128));
-            tma_load_3d(&tmap_d, st, &S->tma_full[stage], ck * 32, t * 128, (int)p, kEvictFirst);
-            tma_load_3d(&tmap_q, st + 2 * kDxBytes, &S->tma_full[stage], ck * 32, 0, (int)p, kEvictLast);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            mbar_wait(&S->raw_empty[stage], phase ^ 1u);
+            uint8_t* st = raws + (size_t)stage * kRawBytes;
+            mbar_arrive_expect_tx(&S->raw_full[stage], (uint32_t)kRawBytes);
+            tma_load_3d(&tmap_d, st, &S->raw_full[stage], ck * 32, t * 128, (int)p, kEvictFirst);
+            tma_load_3d(&tmap_q, st + kDxBytes, &S->raw_full[stage], ck * 32, 0, (int)p, kEvictLast);
+            if (++stage == n_raw) { stage = 0; phase ^= 1u; }
           }
     }
   } else if (warp == 1) {
@@ -143,17 +146,17 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           tc_fence_after_sync();
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
           for (int ck = 0; ck < nch; ++ck) {
-            mbar_wait(&S->conv_done[stage], phase);
+            mbar_wait(&S->op_full[stage], phase);
             tc_fence_after_sync();
-            const uint32_t base = smem_u32(stages + (size_t)stage * kStageBytes);
+            const uint32_t base = smem_u32(ops + (size_t)stage * kOpBytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {  // 32 fp32 / UMMA_K(8)
               const uint64_t bq = make_sw128_kmajor_desc(base + 2 * kDxBytes + k * 32);
               umma_tf32(tmem_d, make_sw128_kmajor_desc(base + k * 32), bq, idesc, (uint32_t)((ck | k) != 0));
               umma_tf32(tmem_d, make_sw128_kmajor_desc(base + kDxBytes + k * 32), bq, idesc, 1u);
             }
-            umma_commit(&S->empty[stage]);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            umma_commit(&S->op_empty[stage]);
+            if (++stage == kOps) { stage = 0; phase ^= 1u; }
           }
           umma_commit(&S->accfull[acc]);
           if (++acc == kAcc) { acc = 0; accphase ^= 1u; }
@@ -165,36 +168,52 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const bool is_q = ct >= 128;
     const int row = is_q ? ct - 128 : ct;     // row inside the tile
     const int sw = row & 7;
-    int stage = 0, acc = 0;
-    uint32_t phase = 0;
+    int rs_ = 0, os_ = 0, acc = 0;      // raw slot, operand slot, accumulator slot
+    uint32_t rphase = 0, ophase = 0;
     for (int64_t p = p_begin; p < p_end; ++p)
       for (int t = 0; t < tiles; ++t) {
         float4 ss4 = make_float4(0.f, 0.f, 0.f, 0.f);  // four partial sums: shorter rounding chains for |x|^2
         for (int ck = 0; ck < nch; ++ck) {
-          mbar_wait(&S->tma_full[stage], phase);
-          uint8_t* st = stages + (size_t)stage * kStageBytes;
-          uint8_t* xrow = (is_q ? st + 2 * kDxBytes : st) + row * 128;
-          uint8_t* lrow = is_q ? st + 2 * kDxBytes + (32 + row) * 128 : st + kDxBytes + row * 128;
+          mbar_wait(&S->raw_full[rs_], rphase);
+          const uint8_t* raw = raws + (size_t)rs_ * kRawBytes;
+          const uint8_t* xrow = (is_q ? raw + kDxBytes : raw) + row * 128;
+          float4 x[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4*>(xrow + ((c ^ sw) << 4));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {  // consumes every loaded value: the loads have landed once this has executed
+            const float4 v = x[c];
+            ss4.x = fmaf(v.x, v.x, ss4.x); ss4.y = fmaf(v.y, v.y, ss4.y); ss4.z = fmaf(v.z, v.z, ss4.z); ss4.w = fmaf(v.w, v.w, ss4.w);
+          }
+          const int raw_slot = rs_;
+          if (++rs_ == n_raw) { rs_ = 0; rphase ^= 1u; }
+          mbar_wait(&S->op_empty[os_], ophase ^ 1u);
+          uint8_t* op = ops + (size_t)os_ * kOpBytes;
+          uint8_t* hrow = is_q ? op + 2 * kDxBytes + row * 128 : op + row * 128;
+          uint8_t* lrow = is_q ? op + 2 * kDxBytes + (32 + row) * 128 : op + kDxBytes + row * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int off = ((c ^ sw) << 4);
-            float4 x = *reinterpret_cast<float4*>(xrow + off);
-            ss4.x = fmaf(x.x, x.x, ss4.x); ss4.y = fmaf(x.y, x.y, ss4.y); ss4.z = fmaf(x.z, x.z, ss4.z); ss4.w = fmaf(x.w, x.w, ss4.w);
+            const float4 v = x[c];
             float4 hi, lo;
-            hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); lo.x = x.x - hi.x;
-            hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); lo.y = x.y - hi.y;
-            hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); lo.z = x.z - hi.z;
-            hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); lo.w = x.w - hi.w;
-            *reinterpret_cast<float4*>(xrow + off) = hi;
+            hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
+            hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
+            hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
+            hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
+            *reinterpret_cast<float4*>(hrow + off) = hi;
             *reinterpret_cast<float4*>(lrow + off) = lo;
           }
           if (ck == nch - 1) {
             const float rs = 1.0f / (sqrtf((ss4.x + ss4.y) + (ss4.z + ss4.w)) + kTinyNorm);
             if (is_q) S->rs_q[acc][row] = rs; else S->rs_d[acc][row] = rs;
           }
+          // Release the raw slot only now: the stores above consumed every loaded value, so the loads have LANDED
+          // (an arrive placed right after the LDS instructions is hoisted above their completion by ptxas -- the
+          // TMA then overwrites rows that are still being read: observed as ~1 % corrupted pairs).
+          mbar_arrive(&S->raw_empty[raw_slot]);
           fence_proxy_async_smem();
-          mbar_arrive(&S->conv_done[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          mbar_arrive(&S->op_full[os_]);
+          if (++os_ == kOps) { os_ = 0; ophase ^= 1u; }
         }
         if (++acc == kAcc) acc = 0;
       }
@@ -309,15 +328,16 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 template <int KB>
 int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& td) {
   const size_t fixed = (size_t)(2 * 128 * 32 + 9 * KB * 32) * sizeof(float) + sizeof(KpShared) + 1024;
-  const int kStages = std::min<int>(kMaxStages, (int)(((size_t)dev.max_smem_optin - fixed) / kStageBytes));
-  const size_t smem = (size_t)kStages * kStageBytes + fixed;
-  if (kStages < 2 || smem > (size_t)dev.max_smem_optin) {
+  const size_t avail = (size_t)dev.max_smem_optin - fixed - (size_t)kOps * kOpBytes;
+  const int n_raw = std::min<int>(kMaxRaw, (int)(avail / kRawBytes));
+  const size_t smem = (size_t)kOps * kOpBytes + (size_t)n_raw * kRawBytes + fixed;
+  if (n_raw < 2 || smem > (size_t)dev.max_smem_optin) {
     set_error("kernel_pool tcgen05: shared-memory plan does not fit");
     return MMB200_ERR_UNSUPPORTED;
   }
   MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(dev.sm_count, P.B);
-  kernel_pool_tc_kernel<KB><<<grid, kThreads, smem, stream>>>(tq, td, P, kStages);
+  kernel_pool_tc_kernel<KB><<<grid, kThreads, smem, stream>>>(tq, td, P, n_raw);
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;
 }

@@ -223,3 +223,17 @@ def test_tcgen05_golden():
                                   alpha=None, log_scale=0.01, want_per_kernel=True, impl="tcgen05")
     assert_close_rel(out["score"], g["score"], what="knrm score")
     assert_close_rel(out["per_kernel"], g["per_kernel"], what="knrm per_kernel")
+
+
+def test_tcgen05_run_to_run_determinism():
+    """Regression: the raw-ring slot used to be released right after the LDS instructions were *issued*; the TMA
+    refilled it before the loads landed and ~1 % of the pairs came out different from run to run."""
+    mu, sg = O.tk_21_kernels()
+    mu, sg = torch.tensor(mu), torch.tensor(sg)
+    w, alpha = torch.linspace(-0.014, 0.014, 21), torch.linspace(0.5, 1.5, 21)
+    q, d, qm, dm = O.synth_kernel_pool_inputs(1000, 30, 200, 300, seed=1236)
+    args = _c(q, d, qm, dm, mu, sg, w)
+    base = interaction.kernel_pool(*args, alpha=alpha.to(DEV), want_per_kernel_query=True, impl="tcgen05")
+    for _ in range(10):
+        o = interaction.kernel_pool(*args, alpha=alpha.to(DEV), want_per_kernel_query=True, impl="tcgen05")
+        assert torch.equal(o["score"], base["score"]) and torch.equal(o["per_kernel_query"], base["per_kernel_query"])
