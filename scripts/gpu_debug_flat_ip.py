@@ -34,6 +34,13 @@ def timing():
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "stage": stage(int(sys.argv[2])); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "timing": timing(); sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "timing1":
+        import torch
+        from matchmaker_b200 import interaction, synthetic as O
+        q, p = O.synth_dense_inputs(6400, 1100000, 768, seed=1)
+        cq, cp = q.cuda(), p.cuda()
+        for _ in range(3): interaction.flat_ip_topk(cq, cp, 100)
+        torch.cuda.synchronize(); sys.exit(0)
     for i in range(len(STAGES)):
         try:
             r = subprocess.run([sys.executable, __file__, "stage", str(i)], timeout=200, capture_output=True, text=True)

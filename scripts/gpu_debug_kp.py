@@ -43,7 +43,33 @@ def timing():
             ms = e0.elapsed_time(e1) / 10
             print(f"timing B={B} Ld={Ld} K={K} {impl}: {ms:.3f} ms -> {B / ms * 1e3 / 1e6:.2f} M pairs/s, {B * bytes_pair / ms * 1e3 / 1e9:.0f} GB/s", flush=True)
 
+def bwd():
+    import torch
+    from matchmaker_b200 import autograd, interaction
+    from oracle import interaction_oracle as O
+    B, Lq, Ld, D, K = 4096, 30, 200, 300, 21
+    mu, sg = O.tk_21_kernels()
+    mu, sg = torch.tensor(mu).cuda(), torch.tensor(sg).cuda()
+    w = torch.linspace(-0.014, 0.014, K).cuda().requires_grad_(True)
+    alpha = torch.linspace(0.5, 1.5, K).cuda().requires_grad_(True)
+    q, d, qm, dm = [t.cuda() for t in O.synth_kernel_pool_inputs(B, Lq, Ld, D, seed=3)]
+    q.requires_grad_(True); d.requires_grad_(True)
+    g = torch.randn(B, device="cuda")
+    def step():
+        s, _ = autograd.kernel_pool(q, d, qm, dm, mu, sg, w, alpha, 1.0)
+        s.backward(g)
+        q.grad = None; d.grad = None; w.grad = None; alpha.grad = None
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"TK fwd+bwd B={B}: {ms:.3f} ms per step -> {B / ms * 1e3 / 1e6:.2f} M pairs/s (forward tcgen05 + backward FFMA)", flush=True)
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "bwd": bwd(); sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "stage": stage(int(sys.argv[2])); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "timing": timing(); sys.exit(0)
     for i in range(len(STAGES)):
