@@ -203,7 +203,7 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int qb = item / P.n_ranges, rg = item % P.n_ranges;
+        const int rg = item / P.n_qblocks, qb = item % P.n_qblocks;  // range-major: co-running CTAs share passages
         const int t0 = rg * P.tiles_per_range, t1 = min(P.n_tiles, t0 + P.tiles_per_range);
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < kblocks; ++kb) {
@@ -223,7 +223,7 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       int stage = 0, acc = 0;
       uint32_t phase = 0, accphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int rg = item % P.n_ranges;
+        const int rg = item / P.n_qblocks;
         const int t0 = rg * P.tiles_per_range, t1 = min(P.n_tiles, t0 + P.tiles_per_range);
         for (int t = t0; t < t1; ++t) {
           mbar_wait(&S->accempty[acc], accphase ^ 1u);
@@ -254,7 +254,7 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     uint2* my_list = P.lists + ((size_t)blockIdx.x * BM + row) * P.cap;
     uint2* warp_lists = P.lists + ((size_t)blockIdx.x * BM + quarter * 32) * P.cap;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int qb = item / P.n_ranges, rg = item % P.n_ranges;
+      const int rg = item / P.n_qblocks, qb = item % P.n_qblocks;  // range-major: co-running CTAs share passages
       const int t0 = rg * P.tiles_per_range, t1 = min(P.n_tiles, t0 + P.tiles_per_range);
       const int64_t q = (int64_t)qb * BM + row;
       const bool live = q < P.nq;
@@ -293,12 +293,19 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
           }
           const uint32_t pbase = (uint32_t)(col0 + c * 32);
+          // steady state: almost no (row, 32-column group) holds a candidate -> one FMNMX3 chain and a skip
+          float gmax = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), __uint_as_float(r[2]));
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(r[j]);
-            bool pass = s >= tau;
-            if (ragged) pass = pass && (int64_t)(pbase + j) < P.n_pass;
-            if (pass) { my_list[cnt] = make_uint2(r[j], pbase + j); ++cnt; }
+          for (int j = 3; j + 1 < 32; j += 2) gmax = fmaxf(fmaxf(gmax, __uint_as_float(r[j])), __uint_as_float(r[j + 1]));
+          gmax = fmaxf(gmax, __uint_as_float(r[31]));
+          if (gmax >= tau) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = __uint_as_float(r[j]);
+              bool pass = s >= tau;
+              if (ragged) pass = pass && (int64_t)(pbase + j) < P.n_pass;
+              if (pass) { my_list[cnt] = make_uint2(r[j], pbase + j); ++cnt; }
+            }
           }
         }
         if (++acc == kAccSlots) { acc = 0; accphase ^= 1u; }
