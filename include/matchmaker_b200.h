@@ -202,6 +202,22 @@ MMB200_API int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
 MMB200_API int mmb200_tkl_top_hills(float* window_score, const float* chunk_scoring, int64_t* top_idx,
                                     float* top15, float* score, int64_t B, int32_t W, void* stream);
 
+/* Backward of the TKL interaction stage (mmb200_tkl_window_scores + mmb200_tkl_top_hills) for
+ * d(loss)/d(score) = grad_score [B]: what autograd derives from sigir20_tkl.py:180-286.  Only the <= 15
+ * gathered windows per document carry gradient.
+ * top_idx [B,3], orig_score [B,W]: outputs of mmb200_tkl_top_hills.
+ * grad_q [B,Lq,D] and grad_chunks [n_chunks,40,D] are overwritten.
+ * grad_params [K + 15 + (saturation == 0 ? 13 + D : K)]: d dense_w | d chunk_scoring | d sat_params |
+ *   d sat_emb_reduce1.weight (embedding saturation only); summed over the batch in a fixed order.
+ * workspace: B * (that length) floats. */
+MMB200_API int mmb200_tkl_bwd(const float* q, const void* q_mask, const float* chunks, const void* chunk_mask,
+                              const int32_t* slot_to_packed, const float* mu, const float* sigma,
+                              const float* dense_w, const float* sat_red_w, const float* sat_params,
+                              const float* chunk_scoring, const int64_t* top_idx, const float* orig_score,
+                              const float* grad_score, float* grad_q, float* grad_chunks, float* grad_params,
+                              float* workspace, int64_t B, int64_t n_chunks, int32_t Lq, int32_t D, int32_t C,
+                              int32_t K, int32_t saturation, int32_t mask_dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Exact maximum-inner-product search with fused per-query top-k (BERT_DOT dense retrieval scoring)
  *

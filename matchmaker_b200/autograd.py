@@ -84,3 +84,38 @@ class _DotPairs(torch.autograd.Function):
 def dot_pairs(qv: torch.Tensor, dv: torch.Tensor) -> torch.Tensor:
     """Differentiable BERT_DOT pair score (bert_dot.py:62)."""
     return _DotPairs.apply(qv, dv)
+
+
+class _TklInteraction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_ctx, q_mask, doc_chunks, chunk_mask, packed, pieces, mu, sigma, dense_w, saturation, sat_params,
+                sat_red_w, chunk_scoring):
+        window = interaction.tkl_window_scores(q_ctx, q_mask, doc_chunks, chunk_mask, packed, pieces, mu, sigma, dense_w,
+                                               saturation, sat_params, sat_red_w)
+        score, orig, top_idx, top15 = interaction.tkl_top_hills(window, chunk_scoring)
+        ctx.save_for_backward(q_ctx, q_mask, doc_chunks, chunk_mask, packed, mu, sigma, dense_w, sat_params,
+                              sat_red_w if sat_red_w is not None else torch.empty(0, device=q_ctx.device),
+                              chunk_scoring, top_idx, orig)
+        ctx.pieces, ctx.saturation, ctx.has_red = pieces, saturation, sat_red_w is not None
+        ctx.mark_non_differentiable(orig, top_idx, top15)
+        return score, orig, top_idx, top15
+
+    @staticmethod
+    def backward(ctx, g_score, _g1, _g2, _g3):
+        (q_ctx, q_mask, doc_chunks, chunk_mask, packed, mu, sigma, dense_w, sat_params, sat_red_w, chunk_scoring, top_idx,
+         orig) = ctx.saved_tensors
+        red = sat_red_w if ctx.has_red else None
+        gq, gc, g_dense, g_cs, g_sat, g_red = interaction.tkl_bwd(q_ctx, q_mask, doc_chunks, chunk_mask, packed, ctx.pieces,
+                                                                  mu, sigma, dense_w, ctx.saturation, sat_params, red,
+                                                                  chunk_scoring, top_idx, orig, g_score)
+        return (gq.to(q_ctx.dtype), None, gc.to(doc_chunks.dtype), None, None, None, None, None, g_dense.view_as(dense_w),
+                None, g_sat.view_as(sat_params), None if g_red is None else g_red.view_as(sat_red_w),
+                g_cs.view_as(chunk_scoring))
+
+
+def tkl_interaction(q_ctx, q_mask, doc_chunks, chunk_mask, packed, pieces, mu, sigma, dense_w, saturation, sat_params,
+                    sat_red_w, chunk_scoring):
+    """Differentiable TKL interaction stage (sigir20_tkl.py:180-286): returns (score [B], orig_score [B,W],
+    top_idx [B,3], top15 [B,15]); gradients flow to q_ctx, doc_chunks, dense_w, sat_params, sat_red_w, chunk_scoring."""
+    return _TklInteraction.apply(q_ctx, q_mask, doc_chunks, chunk_mask, packed, pieces, mu, sigma, dense_w, saturation,
+                                 sat_params, sat_red_w, chunk_scoring)

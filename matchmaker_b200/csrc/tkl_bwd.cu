@@ -45,7 +45,9 @@ template <int KB>
 __global__ void __launch_bounds__(kThreads) tkl_bwd_kernel(TklBwdParams P) {
   extern __shared__ __align__(16) float sm[];
   const int D = P.D, dp = row_stride(D), Lq = P.Lq, K = P.K;
-  float* qs = sm;                              // [40][dp] normalised query rows
+  const float** rowptr = reinterpret_cast<const float**>(sm);          // [32] source row of each window position
+  float** growptr = reinterpret_cast<float**>(sm) + kRows;             // [32] gradient row
+  float* qs = sm + 4 * kRows;                  // [40][dp] normalised query rows (after 64 pointers = 512 B)
   float* ds = qs + (size_t)kMaxLq * dp;        // [32][dp] normalised window rows
   float* gq = ds + (size_t)kRows * dp;         // [40][dp] d(q^) accumulated over the windows
   float* gd = gq + (size_t)kMaxLq * dp;        // [32][dp] d(d^) of the current window
@@ -74,8 +76,6 @@ __global__ void __launch_bounds__(kThreads) tkl_bwd_kernel(TklBwdParams P) {
   float* acc_sat = acc_w + KB;                 // [kNSat + KB] d sat params (embedding: 13; log: K)
   float* gwin = acc_sat + kNSat + KB;          // [16] gradient per gathered slot
   int* win = reinterpret_cast<int*>(gwin + 16);  // [16] window index per slot
-  const float** rowptr = reinterpret_cast<const float**>(win + 16);  // [32] source row of each window position
-  float** growptr = reinterpret_cast<float**>(rowptr + kRows);       // [32] gradient row
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
   if (t < KB) {
@@ -387,7 +387,7 @@ extern "C" int mmb200_tkl_bwd(const float* q, const void* q_mask, const float* c
   const int dp = row_stride(D);
   const size_t floats = (size_t)(2 * kMaxLq + 2 * kRows) * dp + 2 * kMaxLq * 33 + 3 * (size_t)kMaxLq * KB +
                         (size_t)kMaxLq * (kNSat + KB) + 6 * kMaxLq + 3 * kRows + 5 * KB + 16 + KB + (kNSat + KB) + 16 + 16;
-  const size_t need = floats * sizeof(float) + 2 * kRows * sizeof(void*) + 64;
+  const size_t need = floats * sizeof(float) + 4 * kRows * sizeof(float) + 64;
   if (need > (size_t)dev.max_smem_optin) {
     set_error("TKL backward: shared-memory plan does not fit");
     return MMB200_ERR_UNSUPPORTED;

@@ -355,3 +355,43 @@ def topk_merge(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tup
         rc = lib.mmb200_topk_merge(_ptr(cand_scores), _ptr(cand_ids), _ptr(out_s), _ptr(out_i), nq, L, k, _stream(dev))
     _lib.check(rc, "mmb200_topk_merge")
     return out_s, out_i
+
+
+def _tkl_slot_map(packed_indices: torch.Tensor) -> torch.Tensor:
+    pk = packed_indices.reshape(-1).to(torch.int32)
+    return (torch.cumsum(pk, 0, dtype=torch.int32) - 1).masked_fill(pk == 0, -1).contiguous()
+
+
+def tkl_bwd(q_ctx, q_mask, doc_chunks, chunk_mask, packed_indices, chunk_pieces, mu, sigma, dense_weight, saturation,
+            sat_params, sat_red_weight, chunk_scoring, top_idx, orig_score, grad_score):
+    """Gradients of the TKL interaction stage: returns (grad_q_ctx, grad_doc_chunks, grad_dense_weight [K],
+    grad_chunk_scoring [15], grad_sat_params, grad_sat_red_weight or None)."""
+    dev = _require_cuda(q_ctx, doc_chunks, grad_score)
+    q_ctx = q_ctx.float().contiguous()
+    doc_chunks = doc_chunks.float().contiguous()
+    B, Lq, D = q_ctx.shape
+    C = int(chunk_pieces)
+    slot = _tkl_slot_map(packed_indices)
+    q_mask, chunk_mask, mcode = _common_mask_dtype(_prep_mask(q_mask), _prep_mask(chunk_mask))
+    mu, sigma, dense_weight = _f32c(mu).view(-1), _f32c(sigma).view(-1), _f32c(dense_weight).view(-1)
+    sat_params = _f32c(sat_params).view(-1)
+    red = None if sat_red_weight is None else _f32c(sat_red_weight).view(-1)
+    K = mu.numel()
+    sat_code = {"embedding": 0, "log": 1}[saturation]
+    n_sat = 13 if sat_code == 0 else K
+    stride = K + 15 + n_sat + (D if sat_code == 0 else 0)
+    gq = torch.empty_like(q_ctx)
+    gc = torch.empty_like(doc_chunks)
+    gp = torch.empty(stride, dtype=torch.float32, device=dev)
+    ws = torch.empty(max(1, B) * stride, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.mmb200_tkl_bwd(_ptr(q_ctx), _ptr(q_mask), _ptr(doc_chunks), _ptr(chunk_mask), _ptr(slot), _ptr(mu),
+                                _ptr(sigma), _ptr(dense_weight), _ptr(red), _ptr(sat_params),
+                                _ptr(_f32c(chunk_scoring).view(-1)), _ptr(top_idx.contiguous()),
+                                _ptr(orig_score.contiguous()), _ptr(_f32c(grad_score)), _ptr(gq), _ptr(gc), _ptr(gp),
+                                _ptr(ws), B, doc_chunks.shape[0], Lq, D, C, K, sat_code, mcode, _stream(dev))
+    _lib.check(rc, "mmb200_tkl_bwd")
+    g_dense, g_cs, g_sat = gp[:K], gp[K:K + 15], gp[K + 15:K + 15 + n_sat]
+    g_red = gp[K + 15 + n_sat:] if sat_code == 0 else None
+    return gq, gc, g_dense, g_cs, g_sat, g_red

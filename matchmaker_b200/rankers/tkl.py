@@ -2,8 +2,8 @@
 (per-chunk cosine/RBF kernels, sliding-window pooling, saturation, top-3 windows) on the GPU kernels.
 Mirrors matchmaker/models/published/sigir20_tkl.py.
 
-Round-1 scope: inference (forward).  The interaction kernels have no backward yet, so gradients do not
-flow through ``forward`` (the reference trains TKL through autograd of its eager op chain)."""
+Forward and backward of the interaction stage are CUDA kernels (``autograd.tkl_interaction``); gradients reach the
+transformer, the kernel weights and the saturation parameters exactly as through the reference's eager op chain."""
 from __future__ import annotations
 
 from typing import List
@@ -11,7 +11,7 @@ from typing import List
 import torch
 import torch.nn as nn
 
-from .. import interaction
+from .. import autograd
 from .tk import sinusoid_position_features
 
 
@@ -126,11 +126,9 @@ class TKL_sigir20(nn.Module):
         chunk_mask = pad_packed[:, self.overlap:-self.overlap]
 
         sat_params, sat_red = self._saturation_params()
-        with torch.no_grad():
-            window = interaction.tkl_window_scores(query_ctx, query_pad_oov_mask, doc_chunks, chunk_mask, packed,
-                                                   pieces, self.mu, self.sigma, self.dense.weight, self.saturation_type,
-                                                   sat_params, sat_red)
-            score, orig_score, top_idx, top15 = interaction.tkl_top_hills(window, self.chunk_scoring)
+        score, orig_score, top_idx, top15 = autograd.tkl_interaction(
+            query_ctx, query_pad_oov_mask, doc_chunks.contiguous(), chunk_mask.contiguous(), packed, pieces, self.mu,
+            self.sigma, self.dense.weight, self.saturation_type, sat_params, sat_red, self.chunk_scoring)
         if not output_secondary_output:
             return score
         return score, {"score": score, "orig_score": orig_score, "top_non_overlapping_idx": top_idx,

@@ -98,3 +98,88 @@ def test_dropin_class_matches_reference_golden():
                            output_secondary_output=True)
         assert_close_rel(score, g["score"], rel=2e-3, what=f"TKL class score ({sat})")
         assert torch.equal(sec["top_non_overlapping_idx"].cpu(), g["top_non_overlapping_idx"])
+
+
+@pytest.mark.parametrize("sat", ["embedding", "log"])
+def test_backward_vs_fp64_autograd_of_oracle(sat):
+    """Gradients of the TKL interaction stage against torch autograd (fp64) through the oracle restatement."""
+    from matchmaker_b200 import autograd
+    B, Lq, Ld, D, K = 5, 14, 420, 32, 11
+    g = torch.Generator().manual_seed(123)
+    q = torch.randn(B, Lq, D, generator=g) * 0.4
+    d = torch.randn(B, Ld, D, generator=g) * 0.4
+    q_len = torch.tensor([14, 9, 3, 14, 1])
+    d_len = torch.tensor([420, 300, 61, 33, 200])
+    qm = (torch.arange(Lq).unsqueeze(0) < q_len.unsqueeze(1)).float()
+    dm = (torch.arange(Ld).unsqueeze(0) < d_len.unsqueeze(1)).float()
+    q, d = q * qm.unsqueeze(-1), d * dm.unsqueeze(-1)
+    for b in range(B):
+        d[b, 7] = q[b, 0]
+    cd2, cp2, packed, pieces = O.tkl_chunk_documents(d, dm)
+    chunks = cd2[packed][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous()
+    cmask = cp2[packed][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous()
+    params = {"mu": torch.tensor([1.0, 0.9, 0.7, 0.5, 0.3, 0.1, -0.1, -0.3, -0.5, -0.7, -0.9]), "sigma": torch.full((K,), 0.1),
+              "dense_weight": torch.randn(K, generator=g) * 0.1, "chunk_scoring": torch.rand(15, generator=g) + 0.5,
+              "sat_emb_reduce1_weight": torch.randn(D, generator=g) * 0.3,
+              "sat_normer_weight": torch.rand(2, generator=g) + 0.5, "sat_normer_bias": torch.randn(2, generator=g) * 0.1,
+              "saturation_linear_weight": torch.randn(2, generator=g) * 0.5, "saturation_linear_bias": torch.tensor([3.0]),
+              "saturation_linear2_weight": torch.randn(2, generator=g) * 0.2, "saturation_linear2_bias": torch.tensor([2.0]),
+              "saturation_linear3_weight": torch.randn(2, generator=g) * 0.5, "saturation_linear3_bias": torch.tensor([1.0]),
+              "kernel_mult0": torch.rand(K, generator=g) + 0.5}
+    gout = torch.randn(B, generator=g)
+    # fp64 reference gradients through the oracle
+    leaf = {k: v.double().clone().requires_grad_(True) for k, v in params.items() if k not in ("mu", "sigma")}
+    p64 = dict(leaf, mu=params["mu"].double(), sigma=params["sigma"].double())
+    q64 = q.double().clone().requires_grad_(True)
+    c64 = chunks.double().clone().requires_grad_(True)
+    s64, sec64 = O.tkl_interaction(q64, qm.double(), c64, cmask.double(), packed, pieces, p64, sat)
+    s64.backward(gout.double())
+    # CUDA path
+    sp, red = _sat_args(params, sat)
+    cq = q.to(DEV).requires_grad_(True)
+    cc = chunks.to(DEV).requires_grad_(True)
+    cdw = params["dense_weight"].to(DEV).requires_grad_(True)
+    csp = sp.to(DEV).requires_grad_(True)
+    cred = None if red is None else red.to(DEV).requires_grad_(True)
+    ccs = params["chunk_scoring"].to(DEV).requires_grad_(True)
+    score, orig, top_idx, top15 = autograd.tkl_interaction(cq, qm.to(DEV), cc, cmask.to(DEV), packed.to(DEV), pieces,
+                                                           params["mu"].to(DEV), params["sigma"].to(DEV), cdw, sat, csp, cred, ccs)
+    assert torch.equal(top_idx.cpu(), sec64["top_non_overlapping_idx"]), "window selection must agree for the gradient check"
+    assert_close_rel(score, s64.float(), what="score")
+    score.backward(gout.to(DEV))
+
+    def close(a, b, what):
+        a, b = a.double().cpu(), b.double()
+        scale = b.abs().max().item()
+        err = (a - b).abs().max().item()
+        assert err <= 2e-3 * scale + 1e-9, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+
+    close(cq.grad, q64.grad, "grad q_ctx")
+    close(cc.grad, c64.grad, "grad chunks")
+    close(cdw.grad, leaf["dense_weight"].grad, "grad dense")
+    close(ccs.grad, leaf["chunk_scoring"].grad, "grad chunk_scoring")
+    if sat == "embedding":
+        ref_sp = torch.cat([leaf["sat_normer_weight"].grad, leaf["sat_normer_bias"].grad,
+                            leaf["saturation_linear_weight"].grad, leaf["saturation_linear_bias"].grad,
+                            leaf["saturation_linear2_weight"].grad, leaf["saturation_linear2_bias"].grad,
+                            leaf["saturation_linear3_weight"].grad, leaf["saturation_linear3_bias"].grad])
+        close(csp.grad, ref_sp, "grad saturation params")
+        close(cred.grad, leaf["sat_emb_reduce1_weight"].grad, "grad sat_emb_reduce1")
+    else:
+        close(csp.grad, leaf["kernel_mult0"].grad, "grad kernel_mult")
+
+
+def test_tkl_class_trains():
+    from matchmaker_b200.rankers.tkl import TKL_sigir20
+    g = load_golden("tkl_embedding")
+    emb, heads, layers, ff = [int(x) for x in g["cfg"]]
+    params = {k[3:]: v for k, v in g.items() if k.startswith("p__")}
+    m = TKL_sigir20(emb, params["mu"].tolist(), params["sigma"].tolist(), heads, layers, ff, 2000, True, True, "embedding")
+    m.load_state_dict({k[4:]: v for k, v in g.items() if k.startswith("sd__")}, strict=False)
+    m = m.to(DEV).train()
+    s = m(g["q"].to(DEV), g["d"].to(DEV), g["q_mask"].to(DEV), g["d_mask"].to(DEV))
+    s.sum().backward()
+    for name in ("dense.weight", "chunk_scoring", "saturation_linear.weight", "sat_emb_reduce1.weight", "mixer"):
+        p = dict(m.named_parameters())[name]
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0, name
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.contextualizer.parameters())
