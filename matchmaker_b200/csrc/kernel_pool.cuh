@@ -36,5 +36,7 @@ struct KpParams {
 struct DeviceInfo;
 // kernel_pool_tc.cu: *handled = false when the shape is outside the tcgen05 kernel's envelope.
 int kernel_pool_fwd_tc(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, bool* handled);
+// second generation: document operand in tensor memory (kernel_pool_ts.cu); same envelope and outputs
+int kernel_pool_fwd_ts(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, bool* handled);
 
 }  // namespace mmb

@@ -27,6 +27,7 @@
 // Bound: HBM by bytes ((Lq+Ld)*D*4 per pair), co-limited by MUFU ex2 at K=21.  Falls back (handled=false)
 // to the FFMA kernel for Lq > 32, K > 32, or when the cosine matrix itself is requested.
 #include <algorithm>
+#include <cstdlib>
 
 #include "host_util.cuh"
 #include "kernel_pool.cuh"
@@ -39,7 +40,7 @@ namespace {
 
 constexpr int kThreads = 480;
 constexpr int kMaxRaw = 8;            // raw ring (TMA targets): 20 KB per slot
-constexpr int kOps = 2;               // operand ring (what the MMA reads): 40 KB per slot
+constexpr int kMaxOps = 4;            // operand ring (what the MMA reads): 24 KB per slot (40 KB with an explicit hi tile)
 constexpr int kAcc = 4;
 constexpr int kDxBytes = 128 * 128;   // [128 rows][32 fp32]
 constexpr int kQxBytes = 32 * 128;    // [32 query rows][32 fp32]
@@ -55,8 +56,8 @@ constexpr float kClampMin = 1e-10f;
 struct KpShared {
   uint64_t raw_full[kMaxRaw];    // TMA -> convert
   uint64_t raw_empty[kMaxRaw];   // convert (160 arrivals) -> TMA
-  uint64_t op_full[kOps];        // convert (160 arrivals) -> MMA
-  uint64_t op_empty[kOps];       // tcgen05.commit -> convert
+  uint64_t op_full[kMaxOps];     // convert (160 arrivals) -> MMA
+  uint64_t op_empty[kMaxOps];    // tcgen05.commit -> convert
   uint64_t accfull[kAcc];
   uint64_t accempty[kAcc];
   uint32_t tmem_base;
@@ -66,6 +67,7 @@ struct KpShared {
   float mu[32], a[32], alpha[32], w[32];
   float pk[32];
   float qm[32];
+  float lsm[32 * 32];
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -77,17 +79,25 @@ __device__ __forceinline__ float ex2f(float x) {
 template <int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, KpParams P,
-                      int n_raw) {
+                      int n_raw, int raw_hi, int kOps, int ablate, int pf) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment for SWIZZLE_128B tiles, derived by pointer arithmetic on the __shared__ array so the
   // compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ops = smem;                                                          // [kOps][Dhi | Dlo | Q64]
-  uint8_t* raws = smem + kOps * kOpBytes;                                       // [n_raw][Dx | Qx]
+  // raw_hi mode: the MMA reads the document hi operand straight from the raw tile (the tensor core ignores the 13
+  // low mantissa bits of a TF32 operand), so the operand slot only holds Dlo | [Qhi;Qlo] and the raw slot is
+  // released by the MMA's commit instead of by the convert threads
+  const int op_bytes = raw_hi ? kDxBytes + kQ64Bytes : kOpBytes;
+  const int dlo_off = raw_hi ? 0 : kDxBytes;
+  const int q64_off = dlo_off + kDxBytes;
+  uint8_t* raws = smem + kOps * op_bytes;                                       // [n_raw][Dx | Qx]
   float* cs = reinterpret_cast<float*>(raws + (size_t)n_raw * kRawBytes);       // [2][128][32] cosine tiles
-  float* spart = cs + 2 * 128 * 32;                                            // [8][KB][32]
-  float* lsm = spart + 8 * KB * 32;                                            // [KB][32]
-  KpShared* S = reinterpret_cast<KpShared*>(lsm + KB * 32);
+  // the end-of-pair scratch aliases the cosine tiles (free between the last phase B of a pair and the first
+  // phase A of the next one; fenced by named barriers 5 and 4) so that the shared memory goes to raw slots
+  float* spart = cs;                                                           // [8][KB][32]  (<= 32 KB)
+  KpShared* S = reinterpret_cast<KpShared*>(cs + 2 * 128 * 32);
+  float* lsm = S->lsm;                                                         // [KB][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = (P.Ld + 127) / 128;
@@ -99,7 +109,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmap_q);
     prefetch_tensormap(&tmap_d);
-    for (int s = 0; s < n_raw; ++s) { mbar_init(&S->raw_full[s], 1); mbar_init(&S->raw_empty[s], kConvThreads); }
+    for (int s = 0; s < n_raw; ++s) { mbar_init(&S->raw_full[s], 1); mbar_init(&S->raw_empty[s], raw_hi ? 1 : kConvThreads); }
     for (int s = 0; s < kOps; ++s) { mbar_init(&S->op_full[s], kConvThreads); mbar_init(&S->op_empty[s], 1); }
     for (int s = 0; s < kAcc; ++s) { mbar_init(&S->accfull[s], 1); mbar_init(&S->accempty[s], 8); }
     fence_barrier_init();
@@ -123,9 +133,24 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // L2 prefetch cursor: runs `pf` chunk-steps ahead of the shared-memory ring.  The ring alone holds ~100 KB in
+      // flight per SM, not enough to cover the loaded DRAM latency at full bandwidth; the prefetch turns the ring's
+      // loads into L2 hits without spending shared memory.
+      const int per_pair = tiles * nch;
+      const int64_t total = (p_end - p_begin) * per_pair;
+      int64_t pf_step = 0;
+      int pf_ck = 0, pf_t = 0;
+      int64_t pf_p = p_begin;
+      auto prefetch_next = [&]() {
+        tma_prefetch_3d(&tmap_d, pf_ck * 32, pf_t * 128, (int)pf_p);
+        ++pf_step;
+        if (++pf_ck == nch) { pf_ck = 0; if (++pf_t == tiles) { pf_t = 0; ++pf_p; } }
+      };
+      while (pf_step < min((int64_t)pf, total)) prefetch_next();
       for (int64_t p = p_begin; p < p_end; ++p)
         for (int t = 0; t < tiles; ++t)
           for (int ck = 0; ck < nch; ++ck) {
+            if (pf > 0 && pf_step < total) prefetch_next();
             mbar_wait(&S->raw_empty[stage], phase ^ 1u);
             uint8_t* st = raws + (size_t)stage * kRawBytes;
             mbar_arrive_expect_tx(&S->raw_full[stage], (uint32_t)kRawBytes);
@@ -138,7 +163,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     // ------------------------------- MMA issuer ---------------------------------
     if (lane == 0) {
       const uint32_t idesc = make_idesc(kFmtTF32, 128, 64);
-      int stage = 0, acc = 0;
+      int stage = 0, acc = 0, rslot = 0;
       uint32_t phase = 0, accphase = 0;
       for (int64_t p = p_begin; p < p_end; ++p)
         for (int t = 0; t < tiles; ++t) {
@@ -148,13 +173,17 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           for (int ck = 0; ck < nch; ++ck) {
             mbar_wait(&S->op_full[stage], phase);
             tc_fence_after_sync();
-            const uint32_t base = smem_u32(ops + (size_t)stage * kOpBytes);
+            const uint32_t base = smem_u32(ops + (size_t)stage * op_bytes);
+            const uint32_t hi_base = raw_hi ? smem_u32(raws + (size_t)rslot * kRawBytes) : base;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {  // 32 fp32 / UMMA_K(8)
-              const uint64_t bq = make_sw128_kmajor_desc(base + 2 * kDxBytes + k * 32);
-              umma_tf32(tmem_d, make_sw128_kmajor_desc(base + k * 32), bq, idesc, (uint32_t)((ck | k) != 0));
-              umma_tf32(tmem_d, make_sw128_kmajor_desc(base + kDxBytes + k * 32), bq, idesc, 1u);
+              if (ablate & 4) break;  // timing experiment only (MMB200_KP_ABLATE): results are garbage
+              const uint64_t bq = make_sw128_kmajor_desc(base + q64_off + k * 32);
+              umma_tf32(tmem_d, make_sw128_kmajor_desc(hi_base + k * 32), bq, idesc, (uint32_t)((ck | k) != 0));
+              umma_tf32(tmem_d, make_sw128_kmajor_desc(base + dlo_off + k * 32), bq, idesc, 1u);
             }
+            if (raw_hi) umma_commit(&S->raw_empty[rslot]);
+            if (++rslot == n_raw) rslot = 0;
             umma_commit(&S->op_empty[stage]);
             if (++stage == kOps) { stage = 0; phase ^= 1u; }
           }
@@ -179,7 +208,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           const uint8_t* xrow = (is_q ? raw + kDxBytes : raw) + row * 128;
           float4 x[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4*>(xrow + ((c ^ sw) << 4));
+          for (int c = 0; c < 8; ++c) x[c] = (ablate & 8) ? make_float4(1.f, 2.f, 3.f, 4.f) : *reinterpret_cast<const float4*>(xrow + ((c ^ sw) << 4));
 #pragma unroll
           for (int c = 0; c < 8; ++c) {  // consumes every loaded value: the loads have landed once this has executed
             const float4 v = x[c];
@@ -188,9 +217,10 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           const int raw_slot = rs_;
           if (++rs_ == n_raw) { rs_ = 0; rphase ^= 1u; }
           mbar_wait(&S->op_empty[os_], ophase ^ 1u);
-          uint8_t* op = ops + (size_t)os_ * kOpBytes;
-          uint8_t* hrow = is_q ? op + 2 * kDxBytes + row * 128 : op + row * 128;
-          uint8_t* lrow = is_q ? op + 2 * kDxBytes + (32 + row) * 128 : op + kDxBytes + row * 128;
+          uint8_t* op = ops + (size_t)os_ * op_bytes;
+          uint8_t* hrow = is_q ? op + q64_off + row * 128 : op + row * 128;
+          uint8_t* lrow = is_q ? op + q64_off + (32 + row) * 128 : op + dlo_off + row * 128;
+          const bool write_hi = is_q || !raw_hi;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int off = ((c ^ sw) << 4);
@@ -200,8 +230,8 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
             hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
             hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
-            *reinterpret_cast<float4*>(hrow + off) = hi;
-            *reinterpret_cast<float4*>(lrow + off) = lo;
+            if (write_hi && !(ablate & 8)) *reinterpret_cast<float4*>(hrow + off) = hi;
+            if (!(ablate & 2)) *reinterpret_cast<float4*>(lrow + off) = lo;
           }
           if (ck == nch - 1) {
             const float rs = 1.0f / (sqrtf((ss4.x + ss4.y) + (ss4.z + ss4.w)) + kTinyNorm);
@@ -210,7 +240,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           // Release the raw slot only now: the stores above consumed every loaded value, so the loads have LANDED
           // (an arrive placed right after the LDS instructions is hoisted above their completion by ptxas -- the
           // TMA then overwrites rows that are still being read: observed as ~1 % corrupted pairs).
-          mbar_arrive(&S->raw_empty[raw_slot]);
+          if (!raw_hi) mbar_arrive(&S->raw_empty[raw_slot]);
           fence_proxy_async_smem();
           mbar_arrive(&S->op_full[os_]);
           if (++os_ == kOps) { os_ = 0; ophase ^= 1u; }
@@ -242,7 +272,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         float* cbuf = cs + (tile_seq & 1) * (128 * 32);
         mbar_wait(&S->accfull[acc_slot], accphase);
         tc_fence_after_sync();
-        {  // phase A
+        if (!(ablate & 16)) {  // phase A
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc_slot * 64);
           uint32_t rh[16], rl[16];
           tmem_ld_32x32b_x16(taddr + 16 * h, rh);
@@ -265,6 +295,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             *reinterpret_cast<float4*>(cbuf + row * 32 + phys * 4) = make_float4(v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]);
           }
         }
+        else { __syncwarp(); if (lane == 0) mbar_arrive(&S->accempty[acc_slot]); }
         if (++acc_slot == kAcc) { acc_slot = 0; accphase ^= 1u; }
         named_bar_sync(1, kEpiThreads);
         {  // phase B: lane = query row, this warp's 16 document rows
@@ -272,7 +303,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           for (int rr = 0; rr < 16; ++rr) {
             const int r = ew * 16 + rr;
             const float c = cbuf[r * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)];
-            if (c < 1.0e3f) {  // uniform across the warp: whole rows are masked
+            if (c < 1.0e3f && !(ablate & 1)) {  // uniform across the warp: whole rows are masked
 #pragma unroll
               for (int k = 0; k < KB; ++k) {
                 const float u = (c - S->mu[k]) * S->a[k];
@@ -283,6 +314,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
       }
       // ---- end of pair: S_ik = sum over the 8 warps, log, mask, per-kernel sums, score ----
+      named_bar_sync(5, kEpiThreads);  // every warp is done reading the cosine tiles that spart/lsm alias
 #pragma unroll
       for (int k = 0; k < KB; ++k) spart[(ew * KB + k) * 32 + lane] = acc[k];
       if (ew == 0) S->qm[lane] = (lane < P.Lq && mask_test(qraw, qmt)) ? 1.f : 0.f;
@@ -327,17 +359,31 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
 template <int KB>
 int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& td) {
-  const size_t fixed = (size_t)(2 * 128 * 32 + 9 * KB * 32) * sizeof(float) + sizeof(KpShared) + 1024;
-  const size_t avail = (size_t)dev.max_smem_optin - fixed - (size_t)kOps * kOpBytes;
-  const int n_raw = std::min<int>(kMaxRaw, (int)(avail / kRawBytes));
-  const size_t smem = (size_t)kOps * kOpBytes + (size_t)n_raw * kRawBytes + fixed;
+  static_assert(8 * KB * 32 <= 2 * 128 * 32, "end-of-pair scratch must fit inside the cosine tiles");
+  const size_t fixed = (size_t)(2 * 128 * 32) * sizeof(float) + sizeof(KpShared) + 1024;
+  // hardware fact (measured, profiles/r01_bringup_kernel_pool_tc.log): tcgen05 kind::tf32 ignores the 13 low
+  // mantissa bits of its fp32 inputs, so the raw tile IS the hi operand.  MMB200_KP_RAW_HI=0 restores the explicit
+  // hi tile (identical results).
+  const char* env = getenv("MMB200_KP_RAW_HI");
+  const int raw_hi = (env && env[0] == '0') ? 0 : 1;
+  const size_t op_bytes = raw_hi ? (size_t)kDxBytes + kQ64Bytes : (size_t)kOpBytes;
+  int ablate = 0;
+  if (const char* e4 = getenv("MMB200_KP_ABLATE")) ablate = atoi(e4);
+  int pf = 16;
+  if (const char* e5 = getenv("MMB200_KP_PF")) pf = std::max(0, atoi(e5));
+  int kOps = 3;
+  if (const char* e2 = getenv("MMB200_KP_OPS")) kOps = std::max(2, std::min(kMaxOps, atoi(e2)));
+  const size_t avail = (size_t)dev.max_smem_optin - fixed - (size_t)kOps * op_bytes;
+  int n_raw = std::min<int>(kMaxRaw, (int)(avail / kRawBytes));
+  if (const char* e3 = getenv("MMB200_KP_RAW")) n_raw = std::max(2, std::min(n_raw, atoi(e3)));
+  const size_t smem = (size_t)kOps * op_bytes + (size_t)n_raw * kRawBytes + fixed;
   if (n_raw < 2 || smem > (size_t)dev.max_smem_optin) {
     set_error("kernel_pool tcgen05: shared-memory plan does not fit");
     return MMB200_ERR_UNSUPPORTED;
   }
   MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(dev.sm_count, P.B);
-  kernel_pool_tc_kernel<KB><<<grid, kThreads, smem, stream>>>(tq, td, P, n_raw);
+  kernel_pool_tc_kernel<KB><<<grid, kThreads, smem, stream>>>(tq, td, P, n_raw, raw_hi, kOps, ablate, pf);
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;
 }

@@ -27,13 +27,17 @@ def timing():
     import torch
     from matchmaker_b200 import interaction
     from oracle import interaction_oracle as O
-    for (B, Lq, Ld, D, K) in [(4096, 30, 200, 300, 21), (4096, 30, 180, 300, 11)]:
+    import os
+    shapes = [(4096, 30, 200, 300, 21), (4096, 30, 180, 300, 11)]
+    if os.environ.get("KP_SHAPES"):
+        shapes = [tuple(int(v) for v in sh.split(",")) for sh in os.environ["KP_SHAPES"].split(";")]
+    for (B, Lq, Ld, D, K) in shapes:
         mu, sg = (O.tk_21_kernels() if K == 21 else (O.knrm_kernel_mus(11), O.knrm_kernel_sigmas(11)))
         mu, sg = torch.tensor(mu).cuda(), torch.tensor(sg).cuda()
         w, alpha = torch.linspace(-0.014, 0.014, K).cuda(), torch.linspace(0.5, 1.5, K).cuda()
         q, d, qm, dm = [t.cuda() for t in O.synth_kernel_pool_inputs(B, Lq, Ld, D, seed=3)]
         bytes_pair = (Lq + Ld) * D * 4 + (Lq + Ld) * 4 + 4
-        for impl in ("tcgen05", "simt"):
+        for impl in (("tcgen05",) if os.environ.get("KP_SHAPES") else ("tcgen05", "simt")):
             for _ in range(3): interaction.kernel_pool(q, d, qm, dm, mu, sg, w, alpha=alpha, impl=impl)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -41,7 +45,7 @@ def timing():
             for _ in range(10): interaction.kernel_pool(q, d, qm, dm, mu, sg, w, alpha=alpha, impl=impl)
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
-            print(f"timing B={B} Ld={Ld} K={K} {impl}: {ms:.3f} ms -> {B / ms * 1e3 / 1e6:.2f} M pairs/s, {B * bytes_pair / ms * 1e3 / 1e9:.0f} GB/s", flush=True)
+            print(f"timing B={B} Ld={Ld} D={D} K={K} {impl}: {ms:.3f} ms -> {B / ms * 1e3 / 1e6:.2f} M pairs/s, {B * bytes_pair / ms * 1e3 / 1e9:.0f} GB/s", flush=True)
 
 def bwd():
     import torch
