@@ -5,17 +5,18 @@
 // driven by matchmaker/dense_retrieval.py:328,391.  faiss tiles a cuBLAS GEMM into a score buffer and
 // runs a k-selection kernel over it; here the [queries x passages] score matrix is never written:
 //
-//   flat_ip_tc_kernel   persistent CTAs over work items (block of 128 queries) x (range of passages).
-//       warp 0  TMA producer: per k-block one 16 KB query tile + one 32 KB passage tile (SWIZZLE_128B)
-//       warp 1  tcgen05.mma issuer: D[128 queries x 256 passages] fp32 in TMEM, 2 accumulator slots
-//       warps 2-5 epilogue: thread = query row; tcgen05.ld 32 columns at a time, compare against the row's
-//               running threshold tau (the k-th best seen so far), append survivors to the row's private
-//               candidate list (global memory, L2 resident), and when a list fills up the warp compacts
-//               it cooperatively: 32-step bisection on the order-preserving integer image of the scores
-//               finds the k-th largest, survivors are rewritten in place and tau rises.  tau is also
-//               published per query (atomicMax) so items working on other passage ranges of the same
-//               queries filter harder.  Expected appends per row ~ k * ln(n / k): the epilogue costs a few
-//               hundred instructions per 256-column tile against 6144 MMA cycles.
+//   flat_ip_tc_kernel   persistent CTAs over work items (block of 128 queries) x (range of passages); clusters of 2
+//               CTAs take consecutive query blocks and share every passage tile by TMA multicast.
+//       warp 0  TMA producer: per k-block one 16 KB query tile + this CTA's slice of the 32 KB passage tile
+//       warp 1  tcgen05.mma issuer (whole-warp loop, elect.sync): D[128 queries x 256 passages] fp32 in TMEM, 2 slots
+//       warps 2-5 epilogue: thread = query row; tcgen05.ld 32 columns at a time, FMNMX tree -> sub-group maxima,
+//               compare against the row's running threshold tau (the k-th best seen so far); sub-groups holding a
+//               candidate for SOME row of the warp (~1/3 of them) are scanned with warp-uniform control flow and
+//               predicated stores into the row's private candidate list (global memory, L2 resident).  When a list
+//               fills up the warp compacts it cooperatively: 32-step bisection on the order-preserving integer image
+//               of the scores finds the k-th largest, survivors are rewritten in place and tau rises.  tau is also
+//               published per query (atomicMax) so items working on other passage ranges of the same queries filter
+//               harder.  The per-tile loop must stay inside the instruction cache (compact_row is __noinline__).
 //   topk_merge_kernel   per query: bitonic sort of the candidate lists of all ranges (or, after the NCCL
 //       all-gather, of all ranks) under the total order (score desc, id asc) -> [k] scores + ids.
 //
@@ -26,6 +27,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "host_util.cuh"
@@ -35,7 +37,8 @@ namespace mmb {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kHalves = 1;               // column slices of a tile, each with its own epilogue warps and candidate lists
+constexpr int kThreads = 64 + 128 * kHalves;  // TMA warp, MMA warp, 4 epilogue warps per slice
 constexpr int BM = 128;                 // queries per block (UMMA M)
 constexpr int BN = 256;                 // passages per tile (UMMA N)
 constexpr int kABytes = BM * 128;       // one k-block (64 halfs) of the query tile
@@ -84,8 +87,10 @@ __device__ __forceinline__ int64_t pos_to_id(const FipParams& P, uint32_t pos) {
 // Warp-cooperative compaction of one row's candidate list to its top-k under (score desc, id asc).
 // `list` has `cnt` valid entries (cnt <= 32 * EPL).  Returns the new count (min(cnt, k)) and the key of
 // the k-th best entry in *kth_key (kKeyNegInf if fewer than k entries).
+// __noinline__: the epilogue's per-tile loop has to stay inside the instruction cache.  With this routine inlined (and
+// the column loop unrolled) the loop body streamed ~100 KB of code per tile and ran at IPC 0.03.
 template <int EPL>
-__device__ __forceinline__ int compact_row(const FipParams& P, uint2* list, int cnt, int lane, uint32_t* kth_key) {
+__device__ __noinline__ int compact_row(const FipParams& P, uint2* list, int cnt, int lane, uint32_t* kth_key) {
   uint32_t key[EPL], pos[EPL];
 #pragma unroll
   for (int j = 0; j < EPL; ++j) {
@@ -173,9 +178,29 @@ __device__ __forceinline__ int compact_row(const FipParams& P, uint2* list, int 
   return P.k;
 }
 
-template <int EPL>
+// CL = thread-block cluster size.  The CL CTAs of a cluster work on CL consecutive query blocks against the SAME passage
+// tiles: each CTA fetches 1/CL of every passage tile and multicasts it to the whole cluster, so the L2 -> SM traffic per
+// CTA drops from 48 KB to (16 + 32 / CL) KB per k-block.  At 128 x 256 tiles the kernel is bound by exactly that
+// traffic (7.2 TB/s of L2 reads at 626 TFLOP/s), not by the tensor pipe.  A stage may be refilled only when EVERY CTA
+// of the cluster has consumed it, hence the multicast commit onto all `empty` barriers (count CL).
+// PROF (MMB200_FLATIP_PROF=1): debugging aid, one thread per role of CTA 0 accumulates the cycles it spends blocked
+#define FIP_TIMED(slot, stmt)                                 \
+  do {                                                        \
+    if constexpr (PROF) {                                     \
+      const long long t0_ = clock64();                        \
+      stmt;                                                   \
+      pc[slot] += clock64() - t0_;                            \
+    } else {                                                  \
+      stmt;                                                   \
+    }                                                         \
+  } while (0)
+
+template <int EPL, int CL, bool PROF = false>
 __global__ void __launch_bounds__(kThreads, 1)
-flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_p, FipParams P) {
+flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_p, FipParams P,
+                  long long* prof = nullptr) {
+  long long pc[3] = {0, 0, 0};
+  const long long t_start = PROF ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment for SWIZZLE_128B tiles, derived by pointer arithmetic on the __shared__ array so the
   // compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
@@ -183,78 +208,101 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   FipShared* S = reinterpret_cast<FipShared*>(smem + (size_t)kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = P.dim / 64;
-  const int n_items = P.n_qblocks * P.n_ranges;
+  const int n_qgroups = (P.n_qblocks + CL - 1) / CL;   // CL consecutive query blocks per cluster work item
+  const int n_items = n_qgroups * P.n_ranges;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  constexpr uint16_t kAllCtas = (uint16_t)((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmap_q);
     prefetch_tensormap(&tmap_p);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); }
-    for (int s = 0; s < kAccSlots; ++s) { mbar_init(&S->accfull[s], 1); mbar_init(&S->accempty[s], 4); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], CL); }
+    for (int s = 0; s < kAccSlots; ++s) { mbar_init(&S->accfull[s], 1); mbar_init(&S->accempty[s], 4 * kHalves); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&S->tmem_base, 512);
   tc_fence_before_sync();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // peers signal our barriers: their init must be visible cluster-wide
   tc_fence_after_sync();
   const uint32_t tmem_base = S->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // the whole warp walks the loop (uniform control flow and operands); one elected lane issues the TMA: inside an
+    // `if (lane == 0)` region the compiler wraps every TMA / MMA in an ELECT / R2UR waterfall loop (ptx.cuh)
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int rg = item / P.n_qblocks, qb = item % P.n_qblocks;  // range-major: co-running CTAs share passages
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int rg = item / n_qgroups, qb = (item % n_qgroups) * CL + rank;  // range-major: co-running CTAs share passages
         const int t0 = rg * P.tiles_per_range, t1 = min(P.n_tiles, t0 + P.tiles_per_range);
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(&S->empty[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&S->full[stage], (uint32_t)kStageBytes);
+            FIP_TIMED(0, mbar_wait(&S->empty[stage], phase ^ 1u));
             uint8_t* st = smem + (size_t)stage * kStageBytes;
-            tma_load_2d(&tmap_q, st, &S->full[stage], kb * 64, qb * BM, kEvictLast);
-            tma_load_2d(&tmap_p, st + kABytes, &S->full[stage], kb * 64, t * BN, kEvictFirst);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&S->full[stage], (uint32_t)kStageBytes);
+              tma_load_2d(&tmap_q, st, &S->full[stage], kb * 64, qb * BM, kEvictLast);
+              if (CL == 1)
+                tma_load_2d(&tmap_p, st + kABytes, &S->full[stage], kb * 64, t * BN, kEvictFirst);
+              else  // this CTA's slice of the passage tile, written into every CTA of the cluster
+                tma_load_2d_multicast(&tmap_p, st + kABytes + rank * (kBBytes / CL), &S->full[stage], kb * 64,
+                                      t * BN + rank * (BN / CL), kAllCtas, kEvictFirst);
+            }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc((uint32_t)P.fmt, BM, BN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, accphase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int rg = item / P.n_qblocks;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int rg = item / n_qgroups;
         const int t0 = rg * P.tiles_per_range, t1 = min(P.n_tiles, t0 + P.tiles_per_range);
         for (int t = t0; t < t1; ++t) {
-          mbar_wait(&S->accempty[acc], accphase ^ 1u);
+          FIP_TIMED(0, mbar_wait(&S->accempty[acc], accphase ^ 1u));
           tc_fence_after_sync();
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(&S->full[stage], phase);
+            FIP_TIMED(1, mbar_wait(&S->full[stage], phase));
             tc_fence_after_sync();
+            const long long t_i = PROF ? clock64() : 0;
             const uint32_t a = smem_u32(smem + (size_t)stage * kStageBytes);
+            const uint64_t da = make_sw128_kmajor_desc(a), db = make_sw128_kmajor_desc(a + kABytes);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_d, make_sw128_kmajor_desc(a + k * 32), make_sw128_kmajor_desc(a + kABytes + k * 32), idesc,
-                       (uint32_t)((kb | k) != 0));
-            umma_commit(&S->empty[stage]);
+              for (int k = 0; k < 4; ++k)  // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
+                umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+              if (CL == 1) umma_commit(&S->empty[stage]); else umma_commit_multicast(&S->empty[stage], kAllCtas);
+              if (kb == kblocks - 1) umma_commit(&S->accfull[acc]);
+            }
+            __syncwarp();
+            if (PROF) pc[2] += clock64() - t_i;
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(&S->accfull[acc]);
           if (++acc == kAccSlots) { acc = 0; accphase ^= 1u; }
         }
       }
     }
   } else {
     // ------------------------------- epilogue: filter + top-k lists ---------------------------------
+    // Two warps per TMEM lane quarter: warp (quarter, half) filters columns [128 half, 128 half + 128) of every tile into
+    // its own candidate list -- one epilogue warp per scheduler issues too slowly to keep up with the tensor pipe.  The
+    // two halves are published as separate candidate lists; the merge kernel takes any number of them.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;  // query row inside the block == TMEM lane
     int acc = 0;
     uint32_t accphase = 0;
-    uint2* my_list = P.lists + ((size_t)blockIdx.x * BM + row) * P.cap;
-    uint2* warp_lists = P.lists + ((size_t)blockIdx.x * BM + quarter * 32) * P.cap;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int rg = item / P.n_qblocks, qb = item % P.n_qblocks;  // range-major: co-running CTAs share passages
+    long long px[4] = {0, 0, 0, 0};
+    uint2* my_list = P.lists + (((size_t)blockIdx.x * kHalves + half) * BM + row) * P.cap;
+    uint2* warp_lists = P.lists + (((size_t)blockIdx.x * kHalves + half) * BM + quarter * 32) * P.cap;
+    for (int item = cluster_id; item < n_items; item += n_clusters) {
+      const int rg = item / n_qgroups, qb = (item % n_qgroups) * CL + rank;  // range-major: co-running CTAs share passages
       const int t0 = rg * P.tiles_per_range, t1 = min(P.n_tiles, t0 + P.tiles_per_range);
       const int64_t q = (int64_t)qb * BM + row;
       const bool live = q < P.nq;
@@ -263,22 +311,24 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       for (int t = t0; t < t1; ++t) {
         if (live) tau_key = max(tau_key, P.tau_glob[q]);
         float tau = key2f(tau_key);
-        mbar_wait(&S->accfull[acc], accphase);
+        FIP_TIMED(0, mbar_wait(&S->accfull[acc], accphase));
         tc_fence_after_sync();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+        const long long t_e = PROF ? clock64() : 0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / kHalves));
         const int64_t col0 = (int64_t)t * BN;
         const bool ragged = col0 + BN > P.n_pass;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < BN / kHalves / 32; ++c) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
           tmem_ld_wait();
-          if (c == BN / 32 - 1) {  // accumulator fully read: hand the slot back before any slow path
+          if (c == BN / kHalves / 32 - 1) {  // this warp's columns are read: hand the slot back before any slow path
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->accempty[acc]);
           }
           // room for 32 appends per row is guaranteed by compacting whenever cnt > cap - 32
+          const long long t_b = PROF ? clock64() : 0;
           const unsigned full_rows = __ballot_sync(0xffffffffu, cnt > P.cap - 32);
           for (unsigned m = full_rows; m; m &= m - 1) {
             const int rr = __ffs(m) - 1;
@@ -292,24 +342,64 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               atomicMax(P.tau_glob + q, tau_key);
             }
           }
-          const uint32_t pbase = (uint32_t)(col0 + c * 32);
-          // steady state: almost no (row, 32-column group) holds a candidate -> one FMNMX3 chain and a skip
-          float gmax = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), __uint_as_float(r[2]));
+          if (PROF) px[1] += clock64() - t_b;
+          const long long t_c = PROF ? clock64() : 0;
+          const uint32_t pbase = (uint32_t)(col0 + half * (BN / kHalves) + c * 32);
+          // Steady state: a row sees a candidate in ~3 % of its 32-column groups, but SOME row of the warp does in ~90 %
+          // of them, so the path behind the group maximum has to be cheap for the idle lanes too: the group is split in
+          // four sub-groups of 8 whose maxima come out of the same FMNMX chain, and only a sub-group whose maximum
+          // passes is scanned (predicated stores, no per-element branches).
+          float g4[4];
 #pragma unroll
-          for (int j = 3; j + 1 < 32; j += 2) gmax = fmaxf(fmaxf(gmax, __uint_as_float(r[j])), __uint_as_float(r[j + 1]));
-          gmax = fmaxf(gmax, __uint_as_float(r[31]));
-          if (gmax >= tau) {
+          for (int i = 0; i < 4; ++i) {
+            const float m0 = fmaxf(fmaxf(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1])), __uint_as_float(r[8 * i + 2]));
+            const float m1 = fmaxf(fmaxf(__uint_as_float(r[8 * i + 3]), __uint_as_float(r[8 * i + 4])), __uint_as_float(r[8 * i + 5]));
+            g4[i] = fmaxf(fmaxf(m0, m1), fmaxf(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])));
+          }
+          const float gmax = fmaxf(fmaxf(g4[0], g4[1]), fmaxf(g4[2], g4[3]));
+          if (PROF && gmax == 12345.678f) ++px[3];
+          // One warp per scheduler runs this, so dependent chains cost their full latency: the four sub-group votes are
+          // issued back to back, the pass mask is an OR tree and the element select a 3-level tree.  Warp-uniform
+          // control flow only -- per-lane branches here cost a BSSY / BSYNC pair per element.
+          (void)gmax;
+          const unsigned bal[4] = {__ballot_sync(0xffffffffu, g4[0] >= tau), __ballot_sync(0xffffffffu, g4[1] >= tau),
+                                   __ballot_sync(0xffffffffu, g4[2] >= tau), __ballot_sync(0xffffffffu, g4[3] >= tau)};
+          if ((bal[0] | bal[1]) | (bal[2] | bal[3])) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(r[j]);
-              bool pass = s >= tau;
-              if (ragged) pass = pass && (int64_t)(pbase + j) < P.n_pass;
-              if (pass) { my_list[cnt] = make_uint2(r[j], pbase + j); ++cnt; }
+            for (int i = 0; i < 4; ++i) {
+              if (bal[i]) {
+                uint32_t e[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  bool pass = __uint_as_float(r[8 * i + j]) >= tau;
+                  if (ragged) pass = pass && (int64_t)(pbase + 8 * i + j) < P.n_pass;
+                  e[j] = pass ? (1u << j) : 0u;
+                }
+                uint32_t m = ((e[0] | e[1]) | (e[2] | e[3])) | ((e[4] | e[5]) | (e[6] | e[7]));
+                if (PROF) ++px[2];
+                while (__any_sync(0xffffffffu, m != 0)) {
+                  const int j = (__ffs(m) - 1) & 7;  // 7 for lanes that are done (not stored)
+                  const uint32_t a01 = (j & 1) ? r[8 * i + 1] : r[8 * i + 0], a23 = (j & 1) ? r[8 * i + 3] : r[8 * i + 2];
+                  const uint32_t a45 = (j & 1) ? r[8 * i + 5] : r[8 * i + 4], a67 = (j & 1) ? r[8 * i + 7] : r[8 * i + 6];
+                  const uint32_t a03 = (j & 2) ? a23 : a01, a47 = (j & 2) ? a67 : a45;
+                  const uint32_t v = (j & 4) ? a47 : a03;
+                  // predicated store, no branch: a per-lane `if` here costs a divergence / reconvergence per iteration
+                  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.v2.u32 [%1], {%2, %3};\n\t}"
+                               ::"r"(m), "l"(my_list + cnt), "r"(v), "r"(pbase + 8 * i + j)
+                               : "memory");
+                  cnt += m != 0 ? 1 : 0;
+                  if (PROF) { ++px[3]; if (m != 0) ++px[0]; }
+                  m &= m - 1;
+                }
+              }
             }
           }
+          if (PROF) pc[2] += clock64() - t_c;
         }
+        if (PROF) pc[1] += clock64() - t_e;
         if (++acc == kAccSlots) { acc = 0; accphase ^= 1u; }
       }
+      const long long t_f = PROF ? clock64() : 0;
       // item done: final compaction of every row, then publish (score, id) candidates for the merge
       __syncwarp();
       for (int rr = 0; rr < 32; ++rr) {
@@ -323,8 +413,8 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
         if (qq < P.nq) {
           const uint2* lst = warp_lists + (size_t)rr * P.cap;
-          float* cs = P.cand_scores + (size_t)qq * P.n_ranges * P.kpad + (size_t)rg * P.kpad;
-          int64_t* ci = P.cand_ids + (size_t)qq * P.n_ranges * P.kpad + (size_t)rg * P.kpad;
+          float* cs = P.cand_scores + ((size_t)qq * P.n_ranges * kHalves + (size_t)rg * kHalves + half) * P.kpad;
+          int64_t* ci = P.cand_ids + ((size_t)qq * P.n_ranges * kHalves + (size_t)rg * kHalves + half) * P.kpad;
           for (int e = lane; e < P.kpad; e += 32) {
             if (e < nc) {
               const uint2 v = lst[e];
@@ -338,16 +428,24 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
         __syncwarp();
       }
+      if (PROF) pc[2] += clock64() - t_f;
     }
+    if (PROF && blockIdx.x == 0 && threadIdx.x == 64) { prof[5] = pc[0]; prof[6] = pc[1]; prof[7] = pc[2]; prof[8] = px[0]; prof[9] = px[1]; prof[10] = px[2]; prof[11] = px[3]; }
+  }
+  if (PROF && blockIdx.x == 0 && lane == 0) {
+    if (warp == 0) prof[0] = pc[0];
+    if (warp == 1) { prof[1] = pc[0]; prof[2] = pc[1]; prof[3] = pc[2]; }
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA may exit while peers still multicast into it
+  if (PROF && blockIdx.x == 0 && threadIdx.x == 0) prof[4] = clock64() - t_start;
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
   }
 }
+#undef FIP_TIMED
 
 // ---------------------------------------------------------------------------------------------
 // merge: per query, sort L candidates by (score desc, id asc), emit the first k.
@@ -405,7 +503,7 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
 }
 
 struct Plan {
-  int n_qblocks, n_tiles, n_ranges, tiles_per_range, grid, kpad, cap, epl;
+  int n_qblocks, n_tiles, n_ranges, tiles_per_range, grid, kpad, cap, epl, cl;
 };
 
 Plan make_plan(int64_t nq, int64_t n_pass, int k, int sm_count) {
@@ -415,6 +513,16 @@ Plan make_plan(int64_t nq, int64_t n_pass, int k, int sm_count) {
   pl.kpad = (k + 31) / 32 * 32;
   pl.epl = k <= 128 ? 16 : 32;
   pl.cap = 32 * pl.epl;
+  // cluster size: CTAs of a cluster take consecutive query blocks and share every passage tile by TMA multicast.  A
+  // cluster slot without a query block still runs (its slice of the passage tile is needed by its peers), so only pair
+  // up when little is wasted.  MMB200_FLATIP_CLUSTER overrides (1, 2 or 4).
+  pl.cl = (pl.n_qblocks % 2 == 0 || pl.n_qblocks >= 9) ? 2 : 1;
+  if (const char* env = getenv("MMB200_FLATIP_CLUSTER")) {
+    const int c = atoi(env);
+    if (c == 1 || c == 2 || c == 4) pl.cl = c;
+  }
+  const int n_qgroups = (pl.n_qblocks + pl.cl - 1) / pl.cl;
+  const int max_clusters = std::max(1, sm_count / pl.cl);
   // number of passage ranges: every range restarts its threshold at -inf and pays ~log(range/k) list
   // compactions per query, so take the SMALLEST count whose item grid fills the SMs to >= 88 % (or the best
   // fill available).  MMB200_FLATIP_RANGES overrides it for experiments.
@@ -423,10 +531,10 @@ Plan make_plan(int64_t nq, int64_t n_pass, int k, int sm_count) {
   const int max_r = std::max(1, std::min(kMaxRanges, pl.n_tiles));
   double effs[kMaxRanges + 1];
   for (int r = 1; r <= max_r; ++r) {
-    const int64_t items = (int64_t)pl.n_qblocks * r;
-    const int64_t g = std::min<int64_t>(sm_count, items);
+    const int64_t items = (int64_t)n_qgroups * r;
+    const int64_t g = std::min<int64_t>(max_clusters, items);
     const int64_t waves = (items + g - 1) / g;
-    effs[r] = (double)items / (double)(waves * sm_count);
+    effs[r] = (double)items / (double)(waves * max_clusters);
     if (effs[r] > best_eff + 1e-9) { best_eff = effs[r]; best_r = r; }
   }
   for (int r = 1; r <= max_r; ++r)
@@ -437,16 +545,20 @@ Plan make_plan(int64_t nq, int64_t n_pass, int k, int sm_count) {
   }
   pl.tiles_per_range = (pl.n_tiles + best_r - 1) / best_r;
   pl.n_ranges = (pl.n_tiles + pl.tiles_per_range - 1) / pl.tiles_per_range;
-  pl.grid = (int)std::min<int64_t>(sm_count, (int64_t)pl.n_qblocks * pl.n_ranges);
+  pl.grid = pl.cl * (int)std::min<int64_t>(max_clusters, (int64_t)n_qgroups * pl.n_ranges);
   return pl;
 }
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 size_t workspace_bytes(const Plan& pl, int64_t nq) {
-  return align256((size_t)pl.grid * BM * pl.cap * sizeof(uint2)) + align256((size_t)nq * sizeof(uint32_t)) +
-         align256((size_t)nq * pl.n_ranges * pl.kpad * sizeof(float)) +
-         align256((size_t)nq * pl.n_ranges * pl.kpad * sizeof(int64_t));
+  return align256((size_t)nq * sizeof(uint32_t)) + align256((size_t)pl.grid * kHalves * BM * pl.cap * sizeof(uint2)) +
+         align256((size_t)nq * pl.n_ranges * kHalves * pl.kpad * sizeof(float)) +
+         align256((size_t)nq * pl.n_ranges * kHalves * pl.kpad * sizeof(int64_t));
+}
+
+size_t total_workspace_bytes(int64_t nq, int64_t n_pass, int k, int sm_count) {
+  return workspace_bytes(make_plan(nq, n_pass, k, sm_count), nq);
 }
 
 __global__ void fill_u32(uint32_t* p, int64_t n, uint32_t v) {
@@ -479,7 +591,7 @@ extern "C" int64_t mmb200_flat_ip_workspace_bytes(int64_t nq, int64_t n_pass, in
   if (nq <= 0 || n_pass <= 0 || k <= 0 || k > 256) return 0;
   DeviceInfo dev;
   if (current_device_info(&dev)) return -1;
-  return (int64_t)workspace_bytes(make_plan(nq, n_pass, k, dev.sm_count), nq);
+  return (int64_t)total_workspace_bytes(nq, n_pass, k, dev.sm_count);
 }
 
 extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, const int64_t* ids, float* out_scores,
@@ -502,26 +614,10 @@ extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, co
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const Plan pl = make_plan(nq, n_pass, k, dev.sm_count);
-  MMB_REQUIRE((size_t)workspace_bytes_given >= workspace_bytes(pl, nq), "workspace too small (see mmb200_flat_ip_workspace_bytes)");
-
-  FipParams P{};
-  uint8_t* w = static_cast<uint8_t*>(workspace);
-  P.lists = reinterpret_cast<uint2*>(w);
-  w += align256((size_t)pl.grid * BM * pl.cap * sizeof(uint2));
-  P.tau_glob = reinterpret_cast<uint32_t*>(w);
-  w += align256((size_t)nq * sizeof(uint32_t));
-  P.cand_scores = reinterpret_cast<float*>(w);
-  w += align256((size_t)nq * pl.n_ranges * pl.kpad * sizeof(float));
-  P.cand_ids = reinterpret_cast<int64_t*>(w);
-  P.ids = ids; P.id_base = id_base; P.nq = nq; P.n_pass = n_pass; P.dim = dim; P.k = k; P.kpad = pl.kpad; P.cap = pl.cap;
-  P.n_qblocks = pl.n_qblocks; P.n_ranges = pl.n_ranges; P.tiles_per_range = pl.tiles_per_range; P.n_tiles = pl.n_tiles;
-  P.fmt = dtype == MMB200_F16 ? kFmtF16 : kFmtBF16;
-
-  fill_u32<<<64, 256, 0, stream>>>(P.tau_glob, nq, kKeyNegInf);
-  MMB_CHECK_CUDA(cudaGetLastError());
-
+  MMB_REQUIRE((size_t)workspace_bytes_given >= total_workspace_bytes(nq, n_pass, k, dev.sm_count),
+              "workspace too small (see mmb200_flat_ip_workspace_bytes)");
   const CUtensorMapDataType tdt = dtype == MMB200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUtensorMap tq, tp;
+  CUtensorMap tq;
   {
     const uint64_t dims[2] = {(uint64_t)dim, (uint64_t)nq};
     const uint64_t strides[1] = {(uint64_t)dim * 2};
@@ -530,24 +626,80 @@ extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, co
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
       return rc;
   }
-  {
-    const uint64_t dims[2] = {(uint64_t)dim, (uint64_t)n_pass};
-    const uint64_t strides[1] = {(uint64_t)dim * 2};
-    const uint32_t box[2] = {64, BN};
-    if (int rc = encode_tensor_map(&tp, tdt, 2, passages, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
-      return rc;
-  }
-  const size_t smem = (size_t)kStages * kStageBytes + sizeof(FipShared) + 1024;
-  if (pl.epl == 16) {
-    MMB_CHECK_CUDA(cudaFuncSetAttribute(flat_ip_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    flat_ip_tc_kernel<16><<<pl.grid, kThreads, smem, stream>>>(tq, tp, P);
-  } else {
-    MMB_CHECK_CUDA(cudaFuncSetAttribute(flat_ip_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    flat_ip_tc_kernel<32><<<pl.grid, kThreads, smem, stream>>>(tq, tp, P);
-  }
+  uint32_t* tau_glob = static_cast<uint32_t*>(workspace);
+  fill_u32<<<64, 256, 0, stream>>>(tau_glob, nq, kKeyNegInf);
   MMB_CHECK_CUDA(cudaGetLastError());
-  return launch_merge(P.cand_scores, P.cand_ids, nq, pl.n_ranges * pl.kpad, k, out_scores, out_ids, dev, stream);
+
+  // one pass of flat_ip_tc_kernel over `n_rows` passages whose rows are `row_pitch` bytes apart
+  auto run_pass = [&](const Plan& pp, int64_t n_rows, uint64_t row_pitch, const int64_t* pass_ids, int64_t pass_id_base,
+                      FipParams* out_params) -> int {
+    FipParams P{};
+    uint8_t* w = static_cast<uint8_t*>(workspace) + align256((size_t)nq * sizeof(uint32_t));
+    P.tau_glob = tau_glob;
+    P.lists = reinterpret_cast<uint2*>(w);
+    w += align256((size_t)pp.grid * kHalves * BM * pp.cap * sizeof(uint2));
+    P.cand_scores = reinterpret_cast<float*>(w);
+    w += align256((size_t)nq * pp.n_ranges * kHalves * pp.kpad * sizeof(float));
+    P.cand_ids = reinterpret_cast<int64_t*>(w);
+    P.ids = pass_ids; P.id_base = pass_id_base; P.nq = nq; P.n_pass = n_rows; P.dim = dim; P.k = k; P.kpad = pp.kpad; P.cap = pp.cap;
+    P.n_qblocks = pp.n_qblocks; P.n_ranges = pp.n_ranges; P.tiles_per_range = pp.tiles_per_range; P.n_tiles = pp.n_tiles;
+    P.fmt = dtype == MMB200_F16 ? kFmtF16 : kFmtBF16;
+    CUtensorMap tp;
+    {
+      const uint64_t dims[2] = {(uint64_t)dim, (uint64_t)n_rows};
+      const uint64_t strides[1] = {row_pitch};
+      const uint32_t box[2] = {64, (uint32_t)(BN / pp.cl)};   // each CTA of a cluster fetches (and multicasts) its slice
+      if (int rc = encode_tensor_map(&tp, tdt, 2, passages, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
+        return rc;
+    }
+    const size_t smem = (size_t)kStages * kStageBytes + sizeof(FipShared) + 1024;
+    auto launch = [&](auto kernel) -> int {
+      MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)pp.grid);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr{};
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = (unsigned)pp.cl;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      MMB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, tq, tp, P, (long long*)nullptr));
+      return MMB200_OK;
+    };
+    if (out_params) *out_params = P;
+    if (pp.epl == 16 && pp.cl == 1 && out_params && getenv("MMB200_FLATIP_PROF")) {  // debugging aid: per-role wait cycles
+      long long* prof = nullptr;
+      long long h[12] = {0};
+      MMB_CHECK_CUDA(cudaMalloc(&prof, sizeof(h)));
+      MMB_CHECK_CUDA(cudaMemset(prof, 0, sizeof(h)));
+      MMB_CHECK_CUDA(cudaFuncSetAttribute(flat_ip_tc_kernel<16, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      flat_ip_tc_kernel<16, 1, true><<<pp.grid, kThreads, smem, stream>>>(tq, tp, P, prof);
+      MMB_CHECK_CUDA(cudaStreamSynchronize(stream));
+      MMB_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost));
+      MMB_CHECK_CUDA(cudaFree(prof));
+      fprintf(stderr,
+              "fip_prof cycles: total %lld | tma wait_empty %lld | mma wait_accempty %lld wait_full %lld issue %lld | "
+              "epi wait_accfull %lld tile %lld filter+item_end %lld | lane_appends %lld compact %lld subgroup_entries %lld loop_iterations %lld\n",
+              h[4], h[0], h[1], h[2], h[3], h[5], h[6], h[7], h[8], h[9], h[10], h[11]);
+      return MMB200_OK;
+    }
+    if (pp.epl == 16)
+      return pp.cl == 1   ? launch(flat_ip_tc_kernel<16, 1, false>)
+             : pp.cl == 2 ? launch(flat_ip_tc_kernel<16, 2, false>)
+                          : launch(flat_ip_tc_kernel<16, 4, false>);
+    return pp.cl == 1   ? launch(flat_ip_tc_kernel<32, 1, false>)
+           : pp.cl == 2 ? launch(flat_ip_tc_kernel<32, 2, false>)
+                        : launch(flat_ip_tc_kernel<32, 4, false>);
+  };
+
+  FipParams P{};
+  if (int rc = run_pass(pl, n_pass, (uint64_t)dim * 2, ids, id_base, &P)) return rc;
+  return launch_merge(P.cand_scores, P.cand_ids, nq, pl.n_ranges * kHalves * pl.kpad, k, out_scores, out_ids, dev, stream);
 }
 
 extern "C" int mmb200_topk_merge(const float* cand_scores, const int64_t* cand_ids, float* out_scores, int64_t* out_ids,

@@ -268,6 +268,36 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int kRegs>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
+// ---------------------------------------------------------------------------------------------
+// thread-block clusters: rank, cluster-wide barrier, TMA multicast, multicast commit
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster (release / acquire: mbarrier inits and TMEM allocations are visible after it)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one tensor-map box -> the SAME shared-memory offset of every CTA in `cta_mask`; each destination CTA's mbarrier (same
+// offset) receives the complete_tx for the bytes written into it
+__device__ __forceinline__ void tma_load_2d_multicast(const CUtensorMap* map, void* smem_dst, uint64_t* bar, int c0, int c1,
+                                                      uint16_t cta_mask, uint64_t cache_hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5, %6;"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask), "l"(cache_hint)
+      : "memory");
+}
+// tcgen05.commit whose arrival is delivered to the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
 // One lane of a CONVERGED warp.  tcgen05.mma / commit / TMA take their operands from uniform registers: issue them
 // as `if (elect_one_sync()) { ... }` from warp-uniform control flow with operands computed OUTSIDE the branch, so the
 // compiler keeps them uniform.  Inside an `if (lane == 0)` region it cannot prove uniformity and wraps every
