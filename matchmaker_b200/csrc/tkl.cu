@@ -13,6 +13,8 @@
 // 0 become the -9900 sentinel (:257), and window sums are formed directly from the activations (no
 // prefix-difference tricks that would leave round-off residue in empty windows).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "host_util.cuh"
 #include "masks.cuh"
@@ -136,8 +138,18 @@ __device__ __forceinline__ void cos_40x40(const float* __restrict__ qs, const fl
     for (int s = 0; s < 2; ++s) cs[(ti + 10 * r) * 41 + tj + 20 * s] = acc[r][s];
 }
 
-template <int KB>
-__global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
+// PROF (MMB200_TKL_PROF=1): debugging aid, thread 0 of CTA 0 accumulates the cycles of each phase of the chunk loop
+template <int KB, bool PROF = false>
+__global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P, long long* prof = nullptr) {
+  long long pc[5] = {0, 0, 0, 0, 0};
+  long long t_mark = PROF ? clock64() : 0;
+  auto lap = [&](int slot) {
+    if constexpr (PROF) {
+      const long long now = clock64();
+      pc[slot] += now - t_mark;
+      t_mark = now;
+    }
+  };
   extern __shared__ __align__(16) float sm[];
   const int D = P.D, dp = tkl_row_stride(D), Lq = P.Lq, K = P.K;
   float* qs = sm;                                   // [40][dp]  normalised query rows
@@ -181,12 +193,15 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
     for (int c = max(0, c_first - 1); c < c_last; ++c) {
       const int pk_idx = P.slot_to_packed[b * P.C + c];
       __syncthreads();
+      lap(4);
       if (pk_idx >= 0) {
         load_rows_norm(P.chunks + (int64_t)pk_idx * kChunk * D, kChunk, kChunk, D, dp, ds, nullptr, nullptr);
         if (t < kChunk) dm_s[t] = mask_at(P.chunk_mask, P.chunk_mask ? P.mask_dtype : 0, (int64_t)pk_idx * kChunk + t) ? 1.f : 0.f;
         __syncthreads();
+        lap(0);
         cos_40x40(qs, ds, D, dp, cs);
         __syncthreads();
+        lap(1);
       }
       // activations of this chunk's 20 position pairs -> ring
       for (int e = t; e < kMaxLq * kPairsPerChunk; e += kThreads) {
@@ -215,6 +230,7 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
         Z[i * kZStride + slot] = nz;
       }
       __syncthreads();
+      lap(2);
       if (c < c_first) continue;  // halo chunk: nothing to finish
       // windows whose last pair lies in this chunk: w + 14 in [20c, 20c+20)
       const int w_lo = max(0, c * kPairsPerChunk - (kWinPairs - 1));
@@ -270,7 +286,11 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P) {
         for (int k = 0; k < K; ++k) s = fmaf(pk[t * KB + k], w_s[k], s);
         P.window_score[b * P.W + w_lo + t] = s;
       }
+      lap(3);
     }
+  }
+  if (PROF && blockIdx.x == 0 && t == 0) {
+    for (int i = 0; i < 5; ++i) prof[i] = pc[i];
   }
 }
 
@@ -376,12 +396,26 @@ extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int grid = (int)std::min<int64_t>(B * P.segs, (int64_t)dev.sm_count * 2);
+  if (KB == 12 && getenv("MMB200_TKL_PROF")) {
+    long long* prof = nullptr;
+    long long h[5] = {0};
+    MMB_CHECK_CUDA(cudaMalloc(&prof, sizeof(h)));
+    MMB_CHECK_CUDA(cudaMemset(prof, 0, sizeof(h)));
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_window_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    tkl_window_kernel<12, true><<<grid, kThreads, need, stream>>>(P, prof);
+    MMB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    MMB_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost));
+    MMB_CHECK_CUDA(cudaFree(prof));
+    fprintf(stderr, "tkl_prof cycles (CTA 0): load+norm %lld | cosine %lld | activations %lld | windows %lld | other %lld\n", h[0], h[1],
+            h[2], h[3], h[4]);
+    return MMB200_OK;
+  }
   if (KB == 12) {
-    MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_window_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    tkl_window_kernel<12><<<grid, kThreads, need, stream>>>(P);
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_window_kernel<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    tkl_window_kernel<12, false><<<grid, kThreads, need, stream>>>(P, nullptr);
   } else {
-    MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_window_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    tkl_window_kernel<16><<<grid, kThreads, need, stream>>>(P);
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_window_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    tkl_window_kernel<16, false><<<grid, kThreads, need, stream>>>(P, nullptr);
   }
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;

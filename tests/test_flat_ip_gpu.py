@@ -31,7 +31,9 @@ def _check(q, p, ids, k, got_s, got_i):
 
 
 @pytest.mark.parametrize("shape", [(7, 3000, 64, 10), (130, 70000, 128, 100), (64, 20000, 768, 100),
-                                   (5, 300, 64, 128), (200, 5000, 64, 256), (3, 50, 64, 100)])
+                                   (5, 300, 64, 128), (200, 5000, 64, 256), (3, 50, 64, 100),
+                                   # 11 query blocks: clusters of two with one idle slot; 2 blocks, many ranges
+                                   (1300, 6000, 64, 10), (256, 40000, 64, 100)])
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 def test_seeded_vs_oracle(shape, dt):
     nq, n, dim, k = shape
