@@ -206,7 +206,7 @@ class KernelPoolWorkload:
             mu, sg = kernel_mus(11), kernel_sigmas(11)
             self.log_scale, self.alpha = 0.01, None
         self.metric = "query-doc pairs scored/sec (%s cosine + RBF kernel pooling forward, D=300)" % kind.upper()
-        self.kernel = "kernel_pool_tc_kernel"
+        self.kernel = "kernel_pool_ts_kernel"
         self.mu, self.sigma = torch.tensor(mu), torch.tensor(sg)
         self.w = torch.linspace(-0.014, 0.014, len(mu))
         self.q, self.d, self.qm, self.dm = O.synth_kernel_pool_inputs(self.B, self.Lq, self.Ld, self.D, seed=SEED + 10 + rank)
@@ -593,8 +593,9 @@ def main():
                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "note": wl.e2e_note},
                 "gpu_launches": args.steps * (2 if args.workload in ("tkl", "bert_dot") else 1),
                 "roofline": roof}
-        prof = os.path.join(ROOT, "profiles", "maxsim_traffic.json")
-        if args.workload == "colbert" and os.path.isfile(prof):
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+        prof = os.path.join(ROOT, "profiles", "maxsim_traffic.json" if args.workload == "colbert" else f"{args.workload}_traffic.json")
+        if os.path.isfile(prof):
             try:
                 line["roofline"]["traffic"] = json.load(open(prof))["dram_bytes_per_launch"]
             except Exception:

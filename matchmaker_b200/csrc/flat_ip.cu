@@ -37,8 +37,10 @@ namespace mmb {
 
 namespace {
 
-constexpr int kHalves = 1;               // column slices of a tile, each with its own epilogue warps and candidate lists
-constexpr int kThreads = 64 + 128 * kHalves;  // TMA warp, MMA warp, 4 epilogue warps per slice
+constexpr int kEpiPerQuarter = 2;        // epilogue warps per TMEM lane quarter (column halves of a tile, ONE list per row)
+constexpr int kThreads = 64 + 128 * kEpiPerQuarter;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kEPL = 32;                 // list entries per lane in a compaction -> capacity 1024 per row
+constexpr int kCap = 32 * kEPL;
 constexpr int BM = 128;                 // queries per block (UMMA M)
 constexpr int BN = 256;                 // passages per tile (UMMA N)
 constexpr int kABytes = BM * 128;       // one k-block (64 halfs) of the query tile
@@ -55,13 +57,15 @@ struct FipShared {
   uint64_t accempty[kAccSlots];
   uint32_t tmem_base;
   uint32_t pad;
+  int cnt[BM];        // entries in each row's candidate list (appended to by both warps of the row's quarter)
+  uint32_t tau[BM];   // order-preserving image of each row's threshold
 };
 
 struct FipParams {
   const int64_t* ids;       // [n_pass] user ids or nullptr (id = id_base + position)
   int64_t id_base;
   int64_t nq, n_pass;
-  int32_t dim, k, kpad, cap;        // kpad = k rounded up to 32; cap = list capacity per row (32 * EPL)
+  int32_t dim, k, kpad;             // kpad = k rounded up to 32 (list capacity per row is the constant kCap)
   int32_t n_qblocks, n_ranges, tiles_per_range, n_tiles;
   int32_t fmt;
   uint2* lists;             // [grid][BM][cap]  (score bits, position)
@@ -85,12 +89,12 @@ __device__ __forceinline__ int64_t pos_to_id(const FipParams& P, uint32_t pos) {
 }
 
 // Warp-cooperative compaction of one row's candidate list to its top-k under (score desc, id asc).
-// `list` has `cnt` valid entries (cnt <= 32 * EPL).  Returns the new count (min(cnt, k)) and the key of
+// `list` has `cnt` valid entries (cnt <= kCap = 32 * kEPL).  Returns the new count (min(cnt, k)) and the key of
 // the k-th best entry in *kth_key (kKeyNegInf if fewer than k entries).
 // __noinline__: the epilogue's per-tile loop has to stay inside the instruction cache.  With this routine inlined (and
 // the column loop unrolled) the loop body streamed ~100 KB of code per tile and ran at IPC 0.03.
-template <int EPL>
 __device__ __noinline__ int compact_row(const FipParams& P, uint2* list, int cnt, int lane, uint32_t* kth_key) {
+  constexpr int EPL = kEPL;
   uint32_t key[EPL], pos[EPL];
 #pragma unroll
   for (int j = 0; j < EPL; ++j) {
@@ -180,9 +184,8 @@ __device__ __noinline__ int compact_row(const FipParams& P, uint2* list, int cnt
 
 // CL = thread-block cluster size.  The CL CTAs of a cluster work on CL consecutive query blocks against the SAME passage
 // tiles: each CTA fetches 1/CL of every passage tile and multicasts it to the whole cluster, so the L2 -> SM traffic per
-// CTA drops from 48 KB to (16 + 32 / CL) KB per k-block.  At 128 x 256 tiles the kernel is bound by exactly that
-// traffic (7.2 TB/s of L2 reads at 626 TFLOP/s), not by the tensor pipe.  A stage may be refilled only when EVERY CTA
-// of the cluster has consumed it, hence the multicast commit onto all `empty` barriers (count CL).
+// CTA drops from 48 KB to (16 + 32 / CL) KB per k-block (7.2 TB/s of L2 reads at CL = 1).  A stage may be refilled only
+// when EVERY CTA of the cluster has consumed it, hence the multicast commit onto all `empty` barriers (count CL).
 // PROF (MMB200_FLATIP_PROF=1): debugging aid, one thread per role of CTA 0 accumulates the cycles it spends blocked
 #define FIP_TIMED(slot, stmt)                                 \
   do {                                                        \
@@ -195,7 +198,7 @@ __device__ __noinline__ int compact_row(const FipParams& P, uint2* list, int cnt
     }                                                         \
   } while (0)
 
-template <int EPL, int CL, bool PROF = false>
+template <int CL, bool PROF = false>
 __global__ void __launch_bounds__(kThreads, 1)
 flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_p, FipParams P,
                   long long* prof = nullptr) {
@@ -218,7 +221,7 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     prefetch_tensormap(&tmap_q);
     prefetch_tensormap(&tmap_p);
     for (int s = 0; s < kStages; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], CL); }
-    for (int s = 0; s < kAccSlots; ++s) { mbar_init(&S->accfull[s], 1); mbar_init(&S->accempty[s], 4 * kHalves); }
+    for (int s = 0; s < kAccSlots; ++s) { mbar_init(&S->accfull[s], 1); mbar_init(&S->accempty[s], 4 * kEpiPerQuarter); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&S->tmem_base, 512);
@@ -290,65 +293,78 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
   } else {
     // ------------------------------- epilogue: filter + top-k lists ---------------------------------
-    // Two warps per TMEM lane quarter: warp (quarter, half) filters columns [128 half, 128 half + 128) of every tile into
-    // its own candidate list -- one epilogue warp per scheduler issues too slowly to keep up with the tensor pipe.  The
-    // two halves are published as separate candidate lists; the merge kernel takes any number of them.
+    // Two warps per TMEM lane quarter (one epilogue warp per scheduler runs its dependent chains at ~0.2 IPC and cannot
+    // keep up with the tensor pipe): warp (quarter, half) filters columns [128 half, 128 half + 128) of every tile.  Both
+    // append to the SAME per-row list (shared-memory counter, atomicAdd) under the SAME threshold, so nothing about the
+    // selection changes.  The pair meets at a named barrier at the start of every tile: counters are final there, both
+    // warps see the same set of nearly-full rows and split their compaction.  A row gains at most 256 entries per
+    // tile, so compacting when cnt > cap - 256 keeps every append in bounds.
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;  // query row inside the block == TMEM lane
+    const uint32_t pair_bar = 1u + (uint32_t)quarter;
     int acc = 0;
     uint32_t accphase = 0;
-    long long px[4] = {0, 0, 0, 0};
-    uint2* my_list = P.lists + (((size_t)blockIdx.x * kHalves + half) * BM + row) * P.cap;
-    uint2* warp_lists = P.lists + (((size_t)blockIdx.x * kHalves + half) * BM + quarter * 32) * P.cap;
+    uint2* my_list = P.lists + ((size_t)blockIdx.x * BM + row) * kCap;
+    uint2* warp_lists = P.lists + ((size_t)blockIdx.x * BM + quarter * 32) * kCap;
+    int* cnt_s = S->cnt + quarter * 32;
+    uint32_t* tau_s = S->tau + quarter * 32;
+    const uint32_t my_cnt_addr = smem_u32(cnt_s + lane);
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int rg = item / n_qgroups, qb = (item % n_qgroups) * CL + rank;  // range-major: co-running CTAs share passages
       const int t0 = rg * P.tiles_per_range, t1 = min(P.n_tiles, t0 + P.tiles_per_range);
       const int64_t q = (int64_t)qb * BM + row;
       const bool live = q < P.nq;
-      int cnt = 0;
-      uint32_t tau_key = live ? P.tau_glob[q] : 0xffffffffu;  // dead rows accept nothing
+      uint32_t tau_seen = live ? P.tau_glob[q] : 0xffffffffu;  // dead rows accept nothing
+      if (half == 0) { cnt_s[lane] = 0; tau_s[lane] = tau_seen; }
       for (int t = t0; t < t1; ++t) {
-        if (live) tau_key = max(tau_key, P.tau_glob[q]);
-        float tau = key2f(tau_key);
         FIP_TIMED(0, mbar_wait(&S->accfull[acc], accphase));
         tc_fence_after_sync();
         const long long t_e = PROF ? clock64() : 0;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / kHalves));
-        const int64_t col0 = (int64_t)t * BN;
-        const bool ragged = col0 + BN > P.n_pass;
-#pragma unroll 1
-        for (int c = 0; c < BN / kHalves / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          if (c == BN / kHalves / 32 - 1) {  // this warp's columns are read: hand the slot back before any slow path
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S->accempty[acc]);
-          }
-          // room for 32 appends per row is guaranteed by compacting whenever cnt > cap - 32
-          const long long t_b = PROF ? clock64() : 0;
-          const unsigned full_rows = __ballot_sync(0xffffffffu, cnt > P.cap - 32);
-          for (unsigned m = full_rows; m; m &= m - 1) {
+        if (half == 0 && live) tau_s[lane] = max(tau_s[lane], tau_seen);   // other ranges' progress, fetched a tile ago
+        named_bar_sync(pair_bar, 64);      // appends of the previous tile are complete, counters and thresholds final
+        if (live) tau_seen = *reinterpret_cast<volatile const uint32_t*>(P.tau_glob + q);  // consumed one tile later
+        const unsigned full_rows = __ballot_sync(0xffffffffu, cnt_s[lane] > kCap - BN);
+        named_bar_sync(pair_bar, 64);      // both warps have read the counters before either appends to them again
+        if (full_rows) {  // same value in both warps: rows are dealt alternately
+          int idx = 0;
+          for (unsigned m = full_rows; m; m &= m - 1, ++idx) {
+            if ((idx & 1) != half) continue;
             const int rr = __ffs(m) - 1;
-            const int c_rr = __shfl_sync(0xffffffffu, cnt, rr);
             uint32_t kth;
-            const int nc = compact_row<EPL>(P, warp_lists + (size_t)rr * P.cap, c_rr, lane, &kth);
-            if (lane == rr) {
-              cnt = nc;
-              tau_key = max(tau_key, kth);
-              tau = key2f(tau_key);
-              atomicMax(P.tau_glob + q, tau_key);
+            const int nc = compact_row(P, warp_lists + (size_t)rr * kCap, cnt_s[rr], lane, &kth);
+            __syncwarp();
+            if (lane == 0) {
+              cnt_s[rr] = nc;
+              tau_s[rr] = max(tau_s[rr], kth);
+              const int64_t qq = (int64_t)qb * BM + quarter * 32 + rr;
+              if (qq < P.nq) atomicMax(P.tau_glob + qq, kth);
             }
           }
-          if (PROF) px[1] += clock64() - t_b;
-          const long long t_c = PROF ? clock64() : 0;
-          const uint32_t pbase = (uint32_t)(col0 + half * (BN / kHalves) + c * 32);
-          // Steady state: a row sees a candidate in ~3 % of its 32-column groups, but SOME row of the warp does in ~90 %
-          // of them, so the path behind the group maximum has to be cheap for the idle lanes too: the group is split in
-          // four sub-groups of 8 whose maxima come out of the same FMNMX chain, and only a sub-group whose maximum
-          // passes is scanned (predicated stores, no per-element branches).
+          named_bar_sync(pair_bar, 64);
+        }
+        const float tau = key2f(tau_s[lane]);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+        const int64_t col0 = (int64_t)t * BN + half * (BN / 2);
+        const bool ragged = (int64_t)t * BN + BN > P.n_pass;
+        // all 128 columns of this warp into registers, then the accumulator slot goes straight back to the MMA warp:
+        // with two slots the tensor pipe otherwise idles while the filter below works its way through the tile
+        uint32_t r4[BN / 2 / 32][32];
+#pragma unroll
+        for (int c = 0; c < BN / 2 / 32; ++c) tmem_ld_32x32b_x32(taddr + c * 32, r4[c]);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S->accempty[acc]);
+#pragma unroll
+        for (int c = 0; c < BN / 2 / 32; ++c) {
+          uint32_t (&r)[32] = r4[c];
+          const uint32_t pbase = (uint32_t)(col0 + c * 32);
+          // A row sees a candidate in a few % of its 32-column groups, but SOME row of the warp does in most of them,
+          // so the path behind the maxima has to be cheap for the idle lanes too: four sub-groups of 8 whose maxima
+          // come out of one FMNMX tree, votes issued back to back, and only sub-groups with a candidate are scanned --
+          // under warp-uniform control flow (per-lane branches cost a BSSY / BSYNC pair per element) with a
+          // predicated atomic + store.
           float g4[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -356,12 +372,6 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const float m1 = fmaxf(fmaxf(__uint_as_float(r[8 * i + 3]), __uint_as_float(r[8 * i + 4])), __uint_as_float(r[8 * i + 5]));
             g4[i] = fmaxf(fmaxf(m0, m1), fmaxf(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])));
           }
-          const float gmax = fmaxf(fmaxf(g4[0], g4[1]), fmaxf(g4[2], g4[3]));
-          if (PROF && gmax == 12345.678f) ++px[3];
-          // One warp per scheduler runs this, so dependent chains cost their full latency: the four sub-group votes are
-          // issued back to back, the pass mask is an OR tree and the element select a 3-level tree.  Warp-uniform
-          // control flow only -- per-lane branches here cost a BSSY / BSYNC pair per element.
-          (void)gmax;
           const unsigned bal[4] = {__ballot_sync(0xffffffffu, g4[0] >= tau), __ballot_sync(0xffffffffu, g4[1] >= tau),
                                    __ballot_sync(0xffffffffu, g4[2] >= tau), __ballot_sync(0xffffffffu, g4[3] >= tau)};
           if ((bal[0] | bal[1]) | (bal[2] | bal[3])) {
@@ -376,45 +386,41 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                   e[j] = pass ? (1u << j) : 0u;
                 }
                 uint32_t m = ((e[0] | e[1]) | (e[2] | e[3])) | ((e[4] | e[5]) | (e[6] | e[7]));
-                if (PROF) ++px[2];
                 while (__any_sync(0xffffffffu, m != 0)) {
-                  const int j = (__ffs(m) - 1) & 7;  // 7 for lanes that are done (not stored)
+                  const int j = (__ffs(m) - 1) & 7;  // 7 for lanes that are done (nothing stored)
                   const uint32_t a01 = (j & 1) ? r[8 * i + 1] : r[8 * i + 0], a23 = (j & 1) ? r[8 * i + 3] : r[8 * i + 2];
                   const uint32_t a45 = (j & 1) ? r[8 * i + 5] : r[8 * i + 4], a67 = (j & 1) ? r[8 * i + 7] : r[8 * i + 6];
                   const uint32_t a03 = (j & 2) ? a23 : a01, a47 = (j & 2) ? a67 : a45;
                   const uint32_t v = (j & 4) ? a47 : a03;
-                  // predicated store, no branch: a per-lane `if` here costs a divergence / reconvergence per iteration
-                  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.v2.u32 [%1], {%2, %3};\n\t}"
-                               ::"r"(m), "l"(my_list + cnt), "r"(v), "r"(pbase + 8 * i + j)
+                  uint32_t slot;
+                  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.u32 %0, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}"
+                               : "=r"(slot)
+                               : "r"(m), "r"(my_cnt_addr)
                                : "memory");
-                  cnt += m != 0 ? 1 : 0;
-                  if (PROF) { ++px[3]; if (m != 0) ++px[0]; }
+                  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.v2.u32 [%1], {%2, %3};\n\t}"
+                               ::"r"(m), "l"(my_list + slot), "r"(v), "r"(pbase + 8 * i + j)
+                               : "memory");
                   m &= m - 1;
                 }
               }
             }
           }
-          if (PROF) pc[2] += clock64() - t_c;
         }
         if (PROF) pc[1] += clock64() - t_e;
         if (++acc == kAccSlots) { acc = 0; accphase ^= 1u; }
       }
+      // item done: final compaction of every row (split between the two warps), then publish (score, id) candidates
       const long long t_f = PROF ? clock64() : 0;
-      // item done: final compaction of every row, then publish (score, id) candidates for the merge
-      __syncwarp();
-      for (int rr = 0; rr < 32; ++rr) {
-        const int c_rr = __shfl_sync(0xffffffffu, cnt, rr);
+      named_bar_sync(pair_bar, 64);
+      for (int rr = half; rr < 32; rr += 2) {
         uint32_t kth;
-        const int nc = compact_row<EPL>(P, warp_lists + (size_t)rr * P.cap, c_rr, lane, &kth);
+        const int nc = compact_row(P, warp_lists + (size_t)rr * kCap, cnt_s[rr], lane, &kth);
         const int64_t qq = (int64_t)qb * BM + quarter * 32 + rr;
-        if (lane == rr) {
-          cnt = nc;
-          if (live && nc == P.k) atomicMax(P.tau_glob + q, kth);
-        }
         if (qq < P.nq) {
-          const uint2* lst = warp_lists + (size_t)rr * P.cap;
-          float* cs = P.cand_scores + ((size_t)qq * P.n_ranges * kHalves + (size_t)rg * kHalves + half) * P.kpad;
-          int64_t* ci = P.cand_ids + ((size_t)qq * P.n_ranges * kHalves + (size_t)rg * kHalves + half) * P.kpad;
+          if (lane == 0 && nc == P.k) atomicMax(P.tau_glob + qq, kth);
+          const uint2* lst = warp_lists + (size_t)rr * kCap;
+          float* cs = P.cand_scores + (size_t)qq * P.n_ranges * P.kpad + (size_t)rg * P.kpad;
+          int64_t* ci = P.cand_ids + (size_t)qq * P.n_ranges * P.kpad + (size_t)rg * P.kpad;
           for (int e = lane; e < P.kpad; e += 32) {
             if (e < nc) {
               const uint2 v = lst[e];
@@ -428,9 +434,10 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
         __syncwarp();
       }
+      named_bar_sync(pair_bar, 64);   // the counters are reset by the next item only after both warps are done with them
       if (PROF) pc[2] += clock64() - t_f;
     }
-    if (PROF && blockIdx.x == 0 && threadIdx.x == 64) { prof[5] = pc[0]; prof[6] = pc[1]; prof[7] = pc[2]; prof[8] = px[0]; prof[9] = px[1]; prof[10] = px[2]; prof[11] = px[3]; }
+    if (PROF && blockIdx.x == 0 && threadIdx.x == 64) { prof[5] = pc[0]; prof[6] = pc[1]; prof[7] = pc[2]; }
   }
   if (PROF && blockIdx.x == 0 && lane == 0) {
     if (warp == 0) prof[0] = pc[0];
@@ -503,7 +510,7 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
 }
 
 struct Plan {
-  int n_qblocks, n_tiles, n_ranges, tiles_per_range, grid, kpad, cap, epl, cl;
+  int n_qblocks, n_tiles, n_ranges, tiles_per_range, grid, kpad, cl;
 };
 
 Plan make_plan(int64_t nq, int64_t n_pass, int k, int sm_count) {
@@ -511,8 +518,6 @@ Plan make_plan(int64_t nq, int64_t n_pass, int k, int sm_count) {
   pl.n_qblocks = (int)((nq + BM - 1) / BM);
   pl.n_tiles = (int)((n_pass + BN - 1) / BN);
   pl.kpad = (k + 31) / 32 * 32;
-  pl.epl = k <= 128 ? 16 : 32;
-  pl.cap = 32 * pl.epl;
   // cluster size: CTAs of a cluster take consecutive query blocks and share every passage tile by TMA multicast.  A
   // cluster slot without a query block still runs (its slice of the passage tile is needed by its peers), so only pair
   // up when little is wasted.  MMB200_FLATIP_CLUSTER overrides (1, 2 or 4).
@@ -552,9 +557,9 @@ Plan make_plan(int64_t nq, int64_t n_pass, int k, int sm_count) {
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 size_t workspace_bytes(const Plan& pl, int64_t nq) {
-  return align256((size_t)nq * sizeof(uint32_t)) + align256((size_t)pl.grid * kHalves * BM * pl.cap * sizeof(uint2)) +
-         align256((size_t)nq * pl.n_ranges * kHalves * pl.kpad * sizeof(float)) +
-         align256((size_t)nq * pl.n_ranges * kHalves * pl.kpad * sizeof(int64_t));
+  return align256((size_t)nq * sizeof(uint32_t)) + align256((size_t)pl.grid * BM * kCap * sizeof(uint2)) +
+         align256((size_t)nq * pl.n_ranges * pl.kpad * sizeof(float)) +
+         align256((size_t)nq * pl.n_ranges * pl.kpad * sizeof(int64_t));
 }
 
 size_t total_workspace_bytes(int64_t nq, int64_t n_pass, int k, int sm_count) {
@@ -637,11 +642,11 @@ extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, co
     uint8_t* w = static_cast<uint8_t*>(workspace) + align256((size_t)nq * sizeof(uint32_t));
     P.tau_glob = tau_glob;
     P.lists = reinterpret_cast<uint2*>(w);
-    w += align256((size_t)pp.grid * kHalves * BM * pp.cap * sizeof(uint2));
+    w += align256((size_t)pp.grid * BM * kCap * sizeof(uint2));
     P.cand_scores = reinterpret_cast<float*>(w);
-    w += align256((size_t)nq * pp.n_ranges * kHalves * pp.kpad * sizeof(float));
+    w += align256((size_t)nq * pp.n_ranges * pp.kpad * sizeof(float));
     P.cand_ids = reinterpret_cast<int64_t*>(w);
-    P.ids = pass_ids; P.id_base = pass_id_base; P.nq = nq; P.n_pass = n_rows; P.dim = dim; P.k = k; P.kpad = pp.kpad; P.cap = pp.cap;
+    P.ids = pass_ids; P.id_base = pass_id_base; P.nq = nq; P.n_pass = n_rows; P.dim = dim; P.k = k; P.kpad = pp.kpad;
     P.n_qblocks = pp.n_qblocks; P.n_ranges = pp.n_ranges; P.tiles_per_range = pp.tiles_per_range; P.n_tiles = pp.n_tiles;
     P.fmt = dtype == MMB200_F16 ? kFmtF16 : kFmtBF16;
     CUtensorMap tp;
@@ -672,34 +677,30 @@ extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, co
       return MMB200_OK;
     };
     if (out_params) *out_params = P;
-    if (pp.epl == 16 && pp.cl == 1 && out_params && getenv("MMB200_FLATIP_PROF")) {  // debugging aid: per-role wait cycles
+    if (pp.cl == 1 && out_params && getenv("MMB200_FLATIP_PROF")) {  // debugging aid: per-role wait cycles
       long long* prof = nullptr;
       long long h[12] = {0};
       MMB_CHECK_CUDA(cudaMalloc(&prof, sizeof(h)));
       MMB_CHECK_CUDA(cudaMemset(prof, 0, sizeof(h)));
-      MMB_CHECK_CUDA(cudaFuncSetAttribute(flat_ip_tc_kernel<16, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      flat_ip_tc_kernel<16, 1, true><<<pp.grid, kThreads, smem, stream>>>(tq, tp, P, prof);
+      MMB_CHECK_CUDA(cudaFuncSetAttribute(flat_ip_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      flat_ip_tc_kernel<1, true><<<pp.grid, kThreads, smem, stream>>>(tq, tp, P, prof);
       MMB_CHECK_CUDA(cudaStreamSynchronize(stream));
       MMB_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost));
       MMB_CHECK_CUDA(cudaFree(prof));
       fprintf(stderr,
               "fip_prof cycles: total %lld | tma wait_empty %lld | mma wait_accempty %lld wait_full %lld issue %lld | "
-              "epi wait_accfull %lld tile %lld filter+item_end %lld | lane_appends %lld compact %lld subgroup_entries %lld loop_iterations %lld\n",
-              h[4], h[0], h[1], h[2], h[3], h[5], h[6], h[7], h[8], h[9], h[10], h[11]);
+              "epi wait_accfull %lld tile %lld item_end %lld\n",
+              h[4], h[0], h[1], h[2], h[3], h[5], h[6], h[7]);
       return MMB200_OK;
     }
-    if (pp.epl == 16)
-      return pp.cl == 1   ? launch(flat_ip_tc_kernel<16, 1, false>)
-             : pp.cl == 2 ? launch(flat_ip_tc_kernel<16, 2, false>)
-                          : launch(flat_ip_tc_kernel<16, 4, false>);
-    return pp.cl == 1   ? launch(flat_ip_tc_kernel<32, 1, false>)
-           : pp.cl == 2 ? launch(flat_ip_tc_kernel<32, 2, false>)
-                        : launch(flat_ip_tc_kernel<32, 4, false>);
+    return pp.cl == 1   ? launch(flat_ip_tc_kernel<1, false>)
+           : pp.cl == 2 ? launch(flat_ip_tc_kernel<2, false>)
+                        : launch(flat_ip_tc_kernel<4, false>);
   };
 
   FipParams P{};
   if (int rc = run_pass(pl, n_pass, (uint64_t)dim * 2, ids, id_base, &P)) return rc;
-  return launch_merge(P.cand_scores, P.cand_ids, nq, pl.n_ranges * kHalves * pl.kpad, k, out_scores, out_ids, dev, stream);
+  return launch_merge(P.cand_scores, P.cand_ids, nq, pl.n_ranges * pl.kpad, k, out_scores, out_ids, dev, stream);
 }
 
 extern "C" int mmb200_topk_merge(const float* cand_scores, const int64_t* cand_ids, float* out_scores, int64_t* out_ids,
