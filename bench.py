@@ -591,7 +591,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": pairs_per_step / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "note": wl.e2e_note},
-                "gpu_launches": args.steps * (2 if args.workload in ("tkl", "bert_dot") else 1),
+                "gpu_launches": args.steps * {"tkl": 2, "bert_dot": 3}.get(args.workload, 1),  # tkl: windows + hills; bert_dot: fill, GEMM+top-k, merge
                 "roofline": roof}
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
         prof = os.path.join(ROOT, "profiles", "maxsim_traffic.json" if args.workload == "colbert" else f"{args.workload}_traffic.json")
