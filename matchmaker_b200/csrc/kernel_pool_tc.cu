@@ -1,4 +1,6 @@
-// Cosine + RBF kernel pooling forward (KNRM / TK) on the tensor cores with fp32-grade accuracy.
+// Cosine + RBF kernel pooling forward (KNRM / TK) on the tensor cores with fp32-grade accuracy -- FIRST generation,
+// both MMA operands in shared memory.  Superseded by kernel_pool_ts.cu (document operand in tensor memory); kept behind
+// MMB200_KP_VARIANT=ss as an in-library cross-check and for A/B timing (0.376 ms vs 0.283 ms on the TK shape).
 //
 // The contraction q_i . d_j needs ~1e-7 accuracy (the RBF exponent amplifies cosine error by up to
 // (c-mu)/sigma^2) and there is no fp32 tcgen05.mma kind, so every operand is split
@@ -79,7 +81,7 @@ __device__ __forceinline__ float ex2f(float x) {
 template <int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, KpParams P,
-                      int n_raw, int raw_hi, int kOps, int ablate, int pf) {
+                      int n_raw, int raw_hi, int kOps) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment for SWIZZLE_128B tiles, derived by pointer arithmetic on the __shared__ array so the
   // compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
@@ -133,24 +135,9 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // L2 prefetch cursor: runs `pf` chunk-steps ahead of the shared-memory ring.  The ring alone holds ~100 KB in
-      // flight per SM, not enough to cover the loaded DRAM latency at full bandwidth; the prefetch turns the ring's
-      // loads into L2 hits without spending shared memory.
-      const int per_pair = tiles * nch;
-      const int64_t total = (p_end - p_begin) * per_pair;
-      int64_t pf_step = 0;
-      int pf_ck = 0, pf_t = 0;
-      int64_t pf_p = p_begin;
-      auto prefetch_next = [&]() {
-        tma_prefetch_3d(&tmap_d, pf_ck * 32, pf_t * 128, (int)pf_p);
-        ++pf_step;
-        if (++pf_ck == nch) { pf_ck = 0; if (++pf_t == tiles) { pf_t = 0; ++pf_p; } }
-      };
-      while (pf_step < min((int64_t)pf, total)) prefetch_next();
       for (int64_t p = p_begin; p < p_end; ++p)
         for (int t = 0; t < tiles; ++t)
           for (int ck = 0; ck < nch; ++ck) {
-            if (pf > 0 && pf_step < total) prefetch_next();
             mbar_wait(&S->raw_empty[stage], phase ^ 1u);
             uint8_t* st = raws + (size_t)stage * kRawBytes;
             mbar_arrive_expect_tx(&S->raw_full[stage], (uint32_t)kRawBytes);
@@ -177,7 +164,6 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const uint32_t hi_base = raw_hi ? smem_u32(raws + (size_t)rslot * kRawBytes) : base;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {  // 32 fp32 / UMMA_K(8)
-              if (ablate & 4) break;  // timing experiment only (MMB200_KP_ABLATE): results are garbage
               const uint64_t bq = make_sw128_kmajor_desc(base + q64_off + k * 32);
               umma_tf32(tmem_d, make_sw128_kmajor_desc(hi_base + k * 32), bq, idesc, (uint32_t)((ck | k) != 0));
               umma_tf32(tmem_d, make_sw128_kmajor_desc(base + dlo_off + k * 32), bq, idesc, 1u);
@@ -208,7 +194,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           const uint8_t* xrow = (is_q ? raw + kDxBytes : raw) + row * 128;
           float4 x[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) x[c] = (ablate & 8) ? make_float4(1.f, 2.f, 3.f, 4.f) : *reinterpret_cast<const float4*>(xrow + ((c ^ sw) << 4));
+          for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4*>(xrow + ((c ^ sw) << 4));
 #pragma unroll
           for (int c = 0; c < 8; ++c) {  // consumes every loaded value: the loads have landed once this has executed
             const float4 v = x[c];
@@ -230,8 +216,8 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
             hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
             hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
-            if (write_hi && !(ablate & 8)) *reinterpret_cast<float4*>(hrow + off) = hi;
-            if (!(ablate & 2)) *reinterpret_cast<float4*>(lrow + off) = lo;
+            if (write_hi) *reinterpret_cast<float4*>(hrow + off) = hi;
+            *reinterpret_cast<float4*>(lrow + off) = lo;
           }
           if (ck == nch - 1) {
             const float rs = 1.0f / (sqrtf((ss4.x + ss4.y) + (ss4.z + ss4.w)) + kTinyNorm);
@@ -272,7 +258,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         float* cbuf = cs + (tile_seq & 1) * (128 * 32);
         mbar_wait(&S->accfull[acc_slot], accphase);
         tc_fence_after_sync();
-        if (!(ablate & 16)) {  // phase A
+        {  // phase A
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc_slot * 64);
           uint32_t rh[16], rl[16];
           tmem_ld_32x32b_x16(taddr + 16 * h, rh);
@@ -295,7 +281,6 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             *reinterpret_cast<float4*>(cbuf + row * 32 + phys * 4) = make_float4(v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]);
           }
         }
-        else { __syncwarp(); if (lane == 0) mbar_arrive(&S->accempty[acc_slot]); }
         if (++acc_slot == kAcc) { acc_slot = 0; accphase ^= 1u; }
         named_bar_sync(1, kEpiThreads);
         {  // phase B: lane = query row, this warp's 16 document rows
@@ -303,7 +288,7 @@ kernel_pool_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           for (int rr = 0; rr < 16; ++rr) {
             const int r = ew * 16 + rr;
             const float c = cbuf[r * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)];
-            if (c < 1.0e3f && !(ablate & 1)) {  // uniform across the warp: whole rows are masked
+            if (c < 1.0e3f) {  // uniform across the warp: whole rows are masked
 #pragma unroll
               for (int k = 0; k < KB; ++k) {
                 const float u = (c - S->mu[k]) * S->a[k];
@@ -367,10 +352,6 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
   const char* env = getenv("MMB200_KP_RAW_HI");
   const int raw_hi = (env && env[0] == '0') ? 0 : 1;
   const size_t op_bytes = raw_hi ? (size_t)kDxBytes + kQ64Bytes : (size_t)kOpBytes;
-  int ablate = 0;
-  if (const char* e4 = getenv("MMB200_KP_ABLATE")) ablate = atoi(e4);
-  int pf = 16;
-  if (const char* e5 = getenv("MMB200_KP_PF")) pf = std::max(0, atoi(e5));
   int kOps = 3;
   if (const char* e2 = getenv("MMB200_KP_OPS")) kOps = std::max(2, std::min(kMaxOps, atoi(e2)));
   const size_t avail = (size_t)dev.max_smem_optin - fixed - (size_t)kOps * op_bytes;
@@ -383,7 +364,7 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
   }
   MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(dev.sm_count, P.B);
-  kernel_pool_tc_kernel<KB><<<grid, kThreads, smem, stream>>>(tq, td, P, n_raw, raw_hi, kOps, ablate, pf);
+  kernel_pool_tc_kernel<KB><<<grid, kThreads, smem, stream>>>(tq, td, P, n_raw, raw_hi, kOps);
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;
 }

@@ -108,13 +108,6 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* smem_d
       : "memory");
 }
 
-// L2-only prefetch of one tensor-map box (no shared-memory destination, no completion tracking)
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* smem_dst, uint64_t* bar, int c0,
                                             int c1, uint64_t cache_hint) {
   asm volatile(
