@@ -494,7 +494,15 @@ def main():
     wl = make_workload(args.workload, rank, dev)
     wl.to_device()
 
+    # N > 1: scoring runs on a HIGH-priority stream, the top-k exchange on a normal-priority side stream.  The scoring
+    # kernels are persistent (one CTA per SM, nearly all of its shared memory); if the exchange's kernels (top-k, NCCL
+    # all-gather, merge) win SMs first, the displaced CTAs start late and -- NCCL kernels spin until every rank has
+    # arrived -- the ranks convoy (measured at N = 4: 1.2 ms per step for a 0.52 ms kernel).  With priorities the block
+    # scheduler places the next step's CTAs first and the exchange fills in behind them.
     side = torch.cuda.Stream() if world > 1 else None
+    if world > 1:
+        torch.cuda.synchronize()   # the uploads above ran on the default stream
+        torch.cuda.set_stream(torch.cuda.Stream(priority=-1))
 
     def exchange_async(out):
         """The top-k exchange of step i runs on a side stream and overlaps the scoring kernel of step i+1 (a
