@@ -234,6 +234,11 @@ MMB200_API int mmb200_tkl_bwd(const float* q, const void* q_mask, const float* c
  * 1 <= k <= 256.
  * ------------------------------------------------------------------------------------------ */
 MMB200_API int64_t mmb200_flat_ip_workspace_bytes(int64_t nq, int64_t n_pass, int32_t k);
+/* The work decomposition mmb200_flat_ip_topk uses on a device with `sm_count` SMs (pure host arithmetic, no device
+ * needed): out[0] query blocks of 128, out[1] passage tiles of 256, out[2] passage ranges, out[3] tiles per range,
+ * out[4] grid (CTAs, a multiple of the cluster size), out[5] cluster size, out[6..7] workspace bytes (low, high 32
+ * bits).  Returns 0, or MMB200_ERR_INVALID for sizes mmb200_flat_ip_topk would reject. */
+MMB200_API int mmb200_flat_ip_plan(int64_t nq, int64_t n_pass, int32_t k, int32_t sm_count, int32_t out[8]);
 MMB200_API int mmb200_flat_ip_topk(const void* queries, const void* passages, const int64_t* ids,
                                    float* out_scores, int64_t* out_ids, void* workspace,
                                    int64_t workspace_bytes, int64_t nq, int64_t n_pass, int32_t dim, int32_t k,

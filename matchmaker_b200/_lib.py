@@ -37,6 +37,7 @@ SIGNATURES = {
     "mmb200_tkl_bwd": (_c.c_int, [_vp] * 18 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mmb200_tkl_top_hills": (_c.c_int, [_vp] * 5 + [_i64, _i32, _vp]),
     "mmb200_flat_ip_workspace_bytes": (_i64, [_i64, _i64, _i32]),
+    "mmb200_flat_ip_plan": (_c.c_int, [_i64, _i64, _i32, _i32, _c.POINTER(_i32)]),
     "mmb200_flat_ip_topk": (_c.c_int, [_vp] * 6 + [_i64, _i64, _i64, _i32, _i32, _i32, _i64, _vp]),
     "mmb200_topk_merge": (_c.c_int, [_vp] * 4 + [_i64, _i32, _i32, _vp]),
     "mmb200_dot_pairs": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),

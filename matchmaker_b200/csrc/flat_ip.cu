@@ -599,6 +599,18 @@ extern "C" int64_t mmb200_flat_ip_workspace_bytes(int64_t nq, int64_t n_pass, in
   return (int64_t)total_workspace_bytes(nq, n_pass, k, dev.sm_count);
 }
 
+extern "C" int mmb200_flat_ip_plan(int64_t nq, int64_t n_pass, int32_t k, int32_t sm_count, int32_t out[8]) {
+  using namespace mmb;
+  MMB_REQUIRE(out != nullptr, "null pointer");
+  MMB_REQUIRE(nq > 0 && n_pass > 0 && k >= 1 && k <= 256 && sm_count >= 1, "bad sizes");
+  MMB_REQUIRE(n_pass < (1ll << 32) - 512, "at most 2^32 passages per shard");
+  const Plan pl = make_plan(nq, n_pass, k, sm_count);
+  const uint64_t ws = (uint64_t)workspace_bytes(pl, nq);
+  out[0] = pl.n_qblocks; out[1] = pl.n_tiles; out[2] = pl.n_ranges; out[3] = pl.tiles_per_range; out[4] = pl.grid; out[5] = pl.cl;
+  out[6] = (int32_t)(uint32_t)(ws & 0xffffffffu); out[7] = (int32_t)(uint32_t)(ws >> 32);
+  return MMB200_OK;
+}
+
 extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, const int64_t* ids, float* out_scores,
                                    int64_t* out_ids, void* workspace, int64_t workspace_bytes_given, int64_t nq,
                                    int64_t n_pass, int32_t dim, int32_t k, int32_t dtype, int64_t id_base,

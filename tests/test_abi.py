@@ -49,3 +49,28 @@ def test_fails_loudly_without_gpu():
     lib = _lib.load()
     rc = lib.mmb200_device_info(-1, None, None, None)
     assert rc == _lib.ERR_CUDA and "CUDA" in _lib.last_error()
+
+
+@pytest.mark.parametrize("sm_count", [148, 132, 8, 1])
+def test_flat_ip_plan_invariants(sm_count):
+    """Host-side work decomposition of the exact top-k search (pure arithmetic, runs without a GPU): every passage tile
+    belongs to exactly one range, the grid is a whole number of clusters that fits the device, query blocks are never
+    dropped when clusters are formed, and the workspace covers thresholds, candidate lists and per-range candidates."""
+    lib = _lib.load()
+    out = (ctypes.c_int32 * 8)()
+    for nq in (1, 127, 128, 129, 1300, 6400, 100000):
+        for n_pass in (1, 255, 256, 257, 70000, 1100000, 8800000):
+            for k in (1, 100, 256):
+                assert lib.mmb200_flat_ip_plan(nq, n_pass, k, sm_count, out) == _lib.OK, _lib.last_error()
+                n_qb, n_tiles, n_ranges, tpr, grid, cl, ws_lo, ws_hi = [int(v) for v in out]
+                ws = (ws_lo & 0xffffffff) | ((ws_hi & 0xffffffff) << 32)
+                assert n_qb == (nq + 127) // 128 and n_tiles == (n_pass + 255) // 256
+                assert 1 <= n_ranges <= 32 and n_ranges * tpr >= n_tiles and (n_ranges - 1) * tpr < n_tiles
+                assert cl in (1, 2, 4) and grid >= cl and grid % cl == 0 and grid <= max(cl, sm_count)
+                n_groups = (n_qb + cl - 1) // cl
+                assert grid <= cl * n_groups * n_ranges          # no CTA without a work item
+                assert ws >= nq * 4 + grid * 128 * 1024 * 8      # thresholds + one 1024-entry list per row per CTA
+                kpad = (k + 31) // 32 * 32
+                assert ws >= nq * n_ranges * kpad * 12           # (score, id) candidates per query and range
+    assert lib.mmb200_flat_ip_plan(0, 10, 1, sm_count, out) == _lib.ERR_INVALID
+    assert lib.mmb200_flat_ip_plan(10, 10, 257, sm_count, out) == _lib.ERR_INVALID
