@@ -57,3 +57,18 @@ def test_fixture_regenerates_from_the_reference():
     assert _layout(R.load_knrm(11)) == LAYOUT["knrm_11"]
     assert _layout(R.load_tk(300, MU21, SG21, 10, 2, 300, 200, True, True)) == LAYOUT["tk_emb300_k21_len200"]
     assert _layout(R.load_tkl(300, MU11, SG11, 10, 2, 300, 2000, True, True, "log")) == LAYOUT["tkl_emb300_k11_len2000_log"]
+
+
+def test_from_config_reads_the_reference_keys():
+    """`config["model"]` strings and the config keys each `from_config` reads (models/all.py:141-184, knrm.py:21-22,
+    ecai20_tk.py:22-32, sigir20_tkl.py:17-29): a config written for the reference builds the same module here."""
+    from matchmaker_b200.rankers import get_model_class
+    cfg = {"knrm_kernels": 11, "tk_kernels_mu": MU21, "tk_kernels_sigma": SG21, "tk_att_heads": 10, "tk_att_layer": 2,
+           "tk_att_ff_dim": 300, "max_doc_length": 200, "tk_use_diff_posencoding": True, "tk_mix_hybrid_context": True,
+           "tk_use_pos_encoding": True, "tk_saturation_type": "embedding"}
+    assert _layout(get_model_class("knrm").from_config(cfg, 300)) == LAYOUT["knrm_11"]
+    assert _layout(get_model_class("TK").from_config(cfg, 300)) == LAYOUT["tk_emb300_k21_len200"]
+    cfg_tkl = dict(cfg, tk_kernels_mu=MU11, tk_kernels_sigma=SG11, max_doc_length=2000)
+    assert _layout(get_model_class("TKL").from_config(cfg_tkl, 300)) == LAYOUT["tkl_emb300_k11_len2000_embedding"]
+    with pytest.raises(KeyError):
+        get_model_class("conv_knrm")   # outside the hot path: fails loudly instead of silently substituting
