@@ -9,14 +9,17 @@
 //               CTAs take consecutive query blocks and share every passage tile by TMA multicast.
 //       warp 0  TMA producer: per k-block one 16 KB query tile + this CTA's slice of the 32 KB passage tile
 //       warp 1  tcgen05.mma issuer (whole-warp loop, elect.sync): D[128 queries x 256 passages] fp32 in TMEM, 2 slots
-//       warps 2-5 epilogue: thread = query row; tcgen05.ld 32 columns at a time, FMNMX tree -> sub-group maxima,
-//               compare against the row's running threshold tau (the k-th best seen so far); sub-groups holding a
-//               candidate for SOME row of the warp (~1/3 of them) are scanned with warp-uniform control flow and
-//               predicated stores into the row's private candidate list (global memory, L2 resident).  When a list
-//               fills up the warp compacts it cooperatively: 32-step bisection on the order-preserving integer image
-//               of the scores finds the k-th largest, survivors are rewritten in place and tau rises.  tau is also
-//               published per query (atomicMax) so items working on other passage ranges of the same queries filter
-//               harder.  The per-tile loop must stay inside the instruction cache (compact_row is __noinline__).
+//       warps 2-9 epilogue: two warps per TMEM lane quarter, each filtering one 128-column half of every tile, thread =
+//               query row: tcgen05.ld, FMNMX tree -> maxima of 8-column sub-groups, compare against the row's running
+//               threshold tau (the k-th best seen so far); sub-groups holding a candidate for SOME row of the warp (~1/3
+//               of them) are scanned with warp-uniform control flow and a predicated shared-memory atomic + global
+//               store into the row's candidate list (ONE list per row, capacity 1024, global memory).  The pair of
+//               warps meets at a named barrier at the start of every tile; rows whose list could overflow during the
+//               tile are compacted there (split between the two warps): 32-step bisection on the order-preserving
+//               integer image of the scores finds the k-th largest, survivors are rewritten in place and tau rises.
+//               tau is also published per query (atomicMax) so items working on other passage ranges of the same
+//               queries filter harder.  The per-tile loop must stay inside the instruction cache (compact_row is
+//               __noinline__).
 //   topk_merge_kernel   per query: bitonic sort of the candidate lists of all ranges (or, after the NCCL
 //       all-gather, of all ranks) under the total order (score desc, id asc) -> [k] scores + ids.
 //
