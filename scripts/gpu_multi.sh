@@ -1,7 +1,7 @@
 #!/bin/bash
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/gpu_multi_check.py 2>&1 | grep -v "^W\|^\*\*\*\|OMP_NUM" | tail -6
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/tools/gpu_multi_check.py 2>&1 | grep -v "^W\|^\*\*\*\|OMP_NUM" | tail -6
 for w in colbert bert_dot; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --workload $w --steps 10 --warmup 3 > gpurun_out/bench_${w}_n$N.json 2> gpurun_out/bench_${w}_n$N.err
   python - <<PY

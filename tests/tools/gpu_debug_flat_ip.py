@@ -1,6 +1,6 @@
 """Bring-up of the flat-IP top-k kernel: staged, each stage in a subprocess with a timeout."""
 import os, subprocess, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 STAGES = [(7, 3000, 64, 10), (130, 70000, 128, 100), (64, 20000, 768, 100), (200, 5000, 64, 256)]
 

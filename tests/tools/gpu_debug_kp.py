@@ -1,6 +1,6 @@
 """Bring-up of the tcgen05 kernel-pooling forward: staged parity (each stage in a subprocess) + timing."""
 import os, subprocess, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 STAGES = [(1, 30, 128, 32, 11), (2, 30, 128, 300, 11), (3, 30, 200, 300, 21), (40, 17, 77, 64, 11), (300, 30, 180, 300, 11)]
 

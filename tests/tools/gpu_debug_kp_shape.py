@@ -1,6 +1,6 @@
 """Debug helper: one kernel-pooling shape through the tcgen05 kernels vs the oracle, with error statistics."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from matchmaker_b200 import interaction
 from oracle import interaction_oracle as O

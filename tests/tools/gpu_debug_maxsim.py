@@ -1,15 +1,15 @@
 """GPU bring-up script for the max-sim kernels: staged checks, each in its own subprocess with a timeout
 (a watchdog trap poisons the CUDA context), then a quick timing.  Development tool, not a test.
 
-    python scripts/gpu_debug_maxsim.py            # all stages
-    python scripts/gpu_debug_maxsim.py stage N    # one stage (internal)
+    python tests/tools/gpu_debug_maxsim.py            # all stages
+    python tests/tools/gpu_debug_maxsim.py stage N    # one stage (internal)
 """
 import os
 import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 STAGES = [

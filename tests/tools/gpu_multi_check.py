@@ -1,7 +1,7 @@
 """Run under torchrun on N GPUs: sharded FlatIPIndexer + NCCL top-k exchange vs the single-process oracle,
 and the sharded max-sim re-ranking exchange."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import torch.distributed as dist

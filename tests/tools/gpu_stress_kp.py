@@ -1,5 +1,5 @@
 import sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from matchmaker_b200 import interaction, synthetic as O
 mu, sg = O.tk_21_kernels(); mu, sg = torch.tensor(mu).cuda(), torch.tensor(sg).cuda()
 w = torch.linspace(-0.014, 0.014, 21).cuda(); alpha = torch.linspace(0.5, 1.5, 21).cuda()
