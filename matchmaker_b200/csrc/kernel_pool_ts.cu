@@ -8,7 +8,7 @@
 // What changed is where the operands sit.  The first generation wrote Dhi / Dlo to shared memory and let the
 // tensor core read them back: per 128x32 chunk that is 160 (TMA fill) + 352 (convert LDS/STS) + 384 (MMA operand
 // reads) shared-memory wavefronts, ~900 of the ~900 cycles the chunk may take at HBM speed -- the kernel was bound
-// by the shared-memory data path (profiles/r01_kernel_pool_tc_ablation.md).  Here the convert warps write Dhi / Dlo
+// by the shared-memory data path (profiles/r01_kernel_pool_investigation.md).  Here the convert warps write Dhi / Dlo
 // straight into TMEM with tcgen05.st (thread = document row = TMEM lane) and the MMA takes its A operand from
 // there (tcgen05.mma [d], [a_tmem], b_desc): shared memory only carries the TMA fill, one read of the raw tile and
 // the small query operand -- ~510 wavefronts per chunk.
