@@ -130,26 +130,52 @@ class ClockSampler:
 # HBM-resident inputs, an end-to-end step from pinned host buffers, the CPU oracle step, algorithmic bytes.
 # ------------------------------------------------------------------------------------------------------------
 class ColbertWorkload:
-    """BASELINE config 3: ColBERT max-sim, dim=128, Lq=32, Ld=180, 64 queries x 1000 docs per GPU, fp16."""
+    """BASELINE config 3: ColBERT max-sim, dim=128, Lq=32, Ld=180, 64 queries x 1000 docs per GPU, fp16.
+
+    N > 1 is a sharded search of ONE query set: every rank holds the same 64 queries (seed SEED) and its own
+    1000-document shard per query (seed SEED + 1 + rank); the per-query top-100 is exchanged and merged.
+    Documents are generated on the GPU (unit-norm randn rows, MSMARCO-shaped lengths, zero padding, fp16) so that a
+    rank never holds more than the 2.95 GB fp16 copy in host memory (8 ranks generating 5.9 GB fp32 temporaries each
+    on the host cores is what a shared box does not need); the CPU legs read that same tensor back."""
     name = "colbert_maxsim"
     metric = "query-doc pairs scored/sec (ColBERT max-sim d=128)"
     dtype = "f16"
     kernel = "maxsim_qm_kernel"
     bound = "hbm"
+    launches_per_step = 1
 
     def __init__(self, rank, dev):
         from matchmaker_b200 import synthetic as O
         self.dev = dev
-        self.q, self.d, qm, dm = O.synth_colbert_inputs(N_QUERIES, DOCS_PER_QUERY, LQ, LD, DIM, seed=SEED + rank)
-        self.qm, self.dm = qm, dm
+        self.rank = rank
+        g = torch.Generator().manual_seed(SEED)
+        q = torch.nn.functional.normalize(torch.randn(N_QUERIES, LQ, DIM, generator=g), dim=-1)
+        self.q = q.to(torch.float16)
+        self.qm = torch.ones(N_QUERIES, LQ, dtype=torch.bool)   # MASK-augmented queries are always full length
+        gl = torch.Generator().manual_seed(SEED + 1 + rank)
+        self.d_len = O.synth_lengths(N_QUERIES * DOCS_PER_QUERY, 75.0, 30.0, 10, LD, gl)
         self.pairs = N_QUERIES * DOCS_PER_QUERY
         self.alg_bytes = ALG_BYTES_PER_PAIR * self.pairs
         self.alg_note = "SURVEY 8(d): Ld*dim*2 + 4 + 4 + Lq*dim*2/docs_per_query = %d B/pair" % ALG_BYTES_PER_PAIR
         self.id_base = rank * self.pairs
+        self.d = None
+
+    def _generate_docs(self, dev):
+        n = self.pairs
+        dm = torch.arange(LD, device=dev).unsqueeze(0) < self.d_len.to(dev).unsqueeze(1)
+        d = torch.empty((n, LD, DIM), dtype=torch.float16, device=dev)
+        gg = torch.Generator(device=dev).manual_seed(SEED + 1 + self.rank)
+        step = 8000
+        for lo in range(0, n, step):   # bounded temporaries: 8000 x 180 x 128 fp32 = 737 MB
+            x = torch.randn((min(step, n - lo), LD, DIM), generator=gg, device=dev)
+            x = torch.nn.functional.normalize(x, dim=-1) * dm[lo:lo + step].unsqueeze(-1)
+            d[lo:lo + step] = x.to(torch.float16)
+        return d, dm
 
     def to_device(self):
-        self.cq, self.cd = self.q.to(self.dev), self.d.to(self.dev)
-        self.cqm, self.cdm = self.qm.bool().to(self.dev), self.dm.bool().to(self.dev)
+        dev = self.dev
+        self.cq, self.cqm = self.q.to(dev), self.qm.to(dev)
+        self.cd, self.cdm = self._generate_docs(dev)
 
     def kernel_step(self):
         from matchmaker_b200 import interaction
@@ -159,30 +185,72 @@ class ColbertWorkload:
         from matchmaker_b200 import sharding
         return sharding.topk_all_gather_merge(s.view(N_QUERIES, DOCS_PER_QUERY), TOPK, self.id_base)
 
+    def _host_copy(self):
+        if self.d is not None:
+            return
+        if not hasattr(self, "cd"):
+            # reference arm (no device copy exists): same generator on the GPU when the box has one -- the data are
+            # then identical to the GPU arm's -- else on the host cores
+            gdev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+            d, dm = self._generate_docs(gdev)
+            self.d, self.dm = d.cpu(), dm.cpu()
+            return
+        self.d = torch.empty(self.cd.shape, dtype=self.cd.dtype, pin_memory=True)
+        self.d.copy_(self.cd)
+        self.dm = torch.empty(self.cdm.shape, dtype=torch.bool, pin_memory=True)
+        self.dm.copy_(self.cdm)
+        torch.cuda.synchronize()
+
     def pin(self):
-        self.h = [t.pin_memory() for t in (self.q, self.d, self.qm.bool(), self.dm.bool())]
-        return sum(x.numel() * x.element_size() for x in self.h)
+        """Pinned host buffers of the end-to-end call.  Returns the bytes one e2e step really moves host->device:
+        mmb200_maxsim_fwd_host takes the zero-copy path for pinned documents -- the kernel's TMA reads each document
+        over PCIe in 16-row blocks up to its last unmasked row -- so padding rows never travel."""
+        self._host_copy()
+        self.h = [self.q.pin_memory(), self.d, self.qm.pin_memory(), self.dm]
+        rows16 = ((self.d_len + 15) // 16) * 16
+        fetched = int(rows16.sum().item()) * DIM * 2
+        small = self.h[0].numel() * 2 + self.h[2].numel() + self.h[3].numel()
+        self.h2d_dense = sum(x.numel() * x.element_size() for x in self.h)
+        return fetched + small
 
     def e2e_step(self):
         from matchmaker_b200 import interaction
         return interaction.maxsim_host(*self.h, docs_per_query=DOCS_PER_QUERY, device=self.dev)
 
-    e2e_note = ("mmb200_maxsim_fwd_host: pinned host q/d/masks -> chunked H2D overlapped with the kernel -> D2H "
-                "scores; PCIe-bound")
+    def e2e_pageable_step(self):
+        """Same call on PAGEABLE host tensors: no zero-copy, the library stages 96 MB slabs through its own
+        buffers (cudaMemcpyAsync from pageable memory) -- what a caller that never pins would see."""
+        from matchmaker_b200 import interaction
+        if not hasattr(self, "pg"):
+            self.pg = [x.clone() for x in (self.q, self.d, self.qm, self.dm)]   # clone() of a pinned tensor is pageable
+        return interaction.maxsim_host(*self.pg, docs_per_query=DOCS_PER_QUERY, device=self.dev)
+
+    e2e_note = ("mmb200_maxsim_fwd_host on pinned host tensors: q + masks copied (cudaMemcpyAsync), documents read by the "
+                "kernel's TMA straight from pinned host memory over PCIe (zero-copy, 16-row blocks up to each document's "
+                "last unmasked row), scores copied back; h2d_bytes_per_step counts the bytes that really cross PCIe, "
+                "h2d_bytes_dense is the size of the host tensors; pinning happens once, outside the timed region")
 
     def cpu_prepare(self):
-        self.q32, self.d32 = self.q.float(), self.d.float()  # dense_retrieval.py:406 upcasts the fp16 storage
+        self._host_copy()
+        self.cpu_n = N_QUERIES   # one CPU step = the whole workload (64 000 pairs), as in the GPU arm
+        nd = self.cpu_n * DOCS_PER_QUERY
+        self.q32, self.d32 = self.q[:self.cpu_n].float(), self.d[:nd].float()  # dense_retrieval.py:406 upcasts fp16 storage
+        self.cqm_l, self.cdm_l = self.qm[:self.cpu_n].long(), self.dm[:nd].long()
+
+    def cpu_pairs(self):
+        return self.cpu_n * DOCS_PER_QUERY
 
     def cpu_step(self):
         from oracle import interaction_oracle as O
         with torch.no_grad():
-            return O.maxsim_one_query_many_docs(self.q32, self.d32, self.qm, self.dm, DOCS_PER_QUERY)
+            return O.maxsim_one_query_many_docs(self.q32, self.d32, self.cqm_l, self.cdm_l, DOCS_PER_QUERY)
 
     def config(self, n_gpus):
         return {"workload": self.name, "queries_per_gpu": N_QUERIES, "docs_per_query": DOCS_PER_QUERY, "Lq": LQ,
                 "Ld": LD, "dim": DIM, "storage_dtype": "float16", "mask_dtype": "bool",
                 "pairs_per_step": self.pairs * n_gpus,
-                "sharding": "documents sharded over ranks; per-query top-%d all-gather + merge when N>1" % TOPK,
+                "sharding": "documents sharded over ranks (same 64 queries on every rank); per-query top-%d "
+                            "all-gather + merge when N>1" % TOPK,
                 "l2_policy": "inputs larger than L2 (2.95 GB of documents per GPU per step vs 126 MB L2)"}
 
 
@@ -192,6 +260,7 @@ class KernelPoolWorkload:
     = 16 x the config's batch of 256) so that the inputs (1.1 GB) exceed L2."""
     bound = "hbm"
     dtype = "f32"
+    launches_per_step = 1
 
     def __init__(self, rank, dev, kind):
         from matchmaker_b200 import synthetic as O
@@ -265,6 +334,7 @@ class TklWorkload:
     name = "tkl_window_pool"
     metric = "query-doc pairs scored/sec (TKL chunked kernel pooling + window selection, Ld=2000)"
     kernel = "tkl_window_kernel"
+    launches_per_step = 2   # window scores + top hills
 
     def __init__(self, rank, dev, B=128):
         from matchmaker_b200 import synthetic as O
@@ -356,6 +426,7 @@ class BertDotWorkload:
     name = "bert_dot_flat_ip_topk"
     metric = "query-passage pairs scored/sec (BERT_DOT exact inner-product top-100, dim=768)"
     kernel = "flat_ip_tc_kernel"
+    launches_per_step = 3   # threshold fill, GEMM + top-k, merge
 
     def __init__(self, rank, dev, nq=6400, n_pass=1100000, k=100):
         from matchmaker_b200 import synthetic as O
@@ -409,6 +480,10 @@ class BertDotWorkload:
                 "l2_policy": "passage shard 1.69 GB per GPU, larger than L2"}
 
 
+WORKLOADS = ["colbert", "tk", "knrm", "tkl", "bert_dot"]
+SECONDARY = ["tk", "knrm", "tkl", "bert_dot"]
+
+
 def make_workload(name, rank, dev):
     if name == "colbert":
         return ColbertWorkload(rank, dev)
@@ -421,7 +496,36 @@ def make_workload(name, rank, dev):
     raise SystemExit("unknown workload " + name)
 
 
-def time_cpu(wl, budget_s=12.0, max_reps=50):
+def _cpu_threads():
+    """Threads for the CPU legs.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would throttle the reference
+    arm to one core for N > 1 (round 1: 38.8 k pairs/s at N=2 against 957 k at N=1 on the same box); the CPU arm
+    always asks for every physical core explicitly (MMB200_REF_THREADS overrides)."""
+    env = os.environ.get("MMB200_REF_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False) or 0
+    except Exception:  # noqa: BLE001
+        n = 0
+    if n <= 0:
+        n = max(1, (os.cpu_count() or 2) // 2)
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, n)
+
+
+def _cpu_per_step(wl):
+    return wl.cpu_pairs() if hasattr(wl, "cpu_pairs") else (getattr(wl, "cpu_n", None) or wl.pairs)
+
+
+def time_cpu(wl, budget_s=12.0, max_reps=50, one_thread_budget_s=4.0):
+    """cpu_baseline: the oracle port of the reference's PyTorch path on this host's cores (all physical cores), plus the
+    same step on ONE thread -- the reference's own runner setting (train.py:12 pins OMP_NUM_THREADS=1)."""
+    prev = torch.get_num_threads()
+    torch.set_num_threads(_cpu_threads())
     wl.cpu_prepare()
     wl.cpu_step()  # warm-up
     reps, t_total = 0, 0.0
@@ -430,16 +534,33 @@ def time_cpu(wl, budget_s=12.0, max_reps=50):
         wl.cpu_step()
         t_total += time.perf_counter() - t0
         reps += 1
-    per = wl.cpu_pairs() if hasattr(wl, "cpu_pairs") else (getattr(wl, "cpu_n", None) or wl.pairs)
-    return {"value": per * reps / t_total, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d x %d pairs of this workload through the oracle (torch CPU fp32, %d threads of %d logical cores)"
-                      % (reps, per, torch.get_num_threads(), os.cpu_count())}
+    per = _cpu_per_step(wl)
+    out = {"value": per * reps / t_total, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+           "sample": "%d x %d pairs of this workload through the oracle (torch CPU fp32, %d threads of %d logical cores)"
+                     % (reps, per, torch.get_num_threads(), os.cpu_count())}
+    if one_thread_budget_s > 0:
+        torch.set_num_threads(1)
+        t0 = time.perf_counter()
+        wl.cpu_step()
+        dt = time.perf_counter() - t0
+        n1 = 1
+        while dt < one_thread_budget_s and n1 < 5:
+            t1 = time.perf_counter()
+            wl.cpu_step()
+            dt += time.perf_counter() - t1
+            n1 += 1
+        out["one_thread"] = {"value": per * n1 / dt, "unit": "pairs/s", "cores": 1,
+                             "note": "same step with torch.set_num_threads(1) (the reference runner's OMP_NUM_THREADS=1, train.py:12)"}
+    torch.set_num_threads(prev)
+    return out
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU PyTorch path (oracle port) on this host, rank 0 only."""
+    """--impl reference: the reference's CPU PyTorch path (oracle port) on this host, rank 0 only.  `config` is the GPU
+    arm's config at N=1 verbatim; what one CPU step covers is said in `cpu_baseline.sample`."""
     if rank != 0:
         return
+    torch.set_num_threads(_cpu_threads())
     wl = make_workload(args.workload, 0, torch.device("cpu"))
     wl.cpu_prepare()
     for _ in range(args.warmup):
@@ -448,19 +569,76 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         wl.cpu_step()
     dt = time.perf_counter() - t0
-    per = wl.cpu_pairs() if hasattr(wl, "cpu_pairs") else (getattr(wl, "cpu_n", None) or wl.pairs)
+    per = _cpu_per_step(wl)
     v = per * args.steps / dt
-    cfg = wl.config(1)
-    cfg["pairs_per_step"] = per
-    cfg["reference_step"] = "each step = %d pairs of the workload (bounded CPU sample)" % per
     line = {"impl": "reference", "metric": wl.metric, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(1),
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "each step = %d pairs on %d torch threads (%d logical cores)"
-                                       % (per, torch.get_num_threads(), os.cpu_count())},
+                             "sample": "each step = %d pairs of the workload on %d torch threads (%d logical cores); "
+                                       "under torchrun rank 0 alone runs it" % (per, torch.get_num_threads(), os.cpu_count())},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def _roofline(wl, kern_ms, workload_key):
+    hbm_peak, peak_src = _peaks()
+    if wl.bound == "hbm":
+        achieved = wl.alg_bytes / (kern_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": wl.kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_launch": wl.alg_bytes, "algorithmic_bytes": wl.alg_note}
+    else:
+        tf_peak, tf_src = _tensor_peak()
+        achieved = wl.flops / (kern_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": wl.kernel, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": achieved / tf_peak, "traffic": None, "peak_source": tf_src, "kernel_ms": kern_ms,
+                "algorithmic_flops_per_launch": wl.flops, "algorithmic_flops": wl.alg_note}
+    # DRAM bytes per launch of the dominant kernel: NOT measured in this run (ncu cannot run inside a timed bench) --
+    # copied from the committed `ncu --set full` capture of this workload under profiles/
+    prof = os.path.join(ROOT, "profiles", "maxsim_traffic.json" if workload_key == "colbert" else f"{workload_key}_traffic.json")
+    if os.path.isfile(prof):
+        try:
+            j = json.load(open(prof))
+            roof["traffic"] = j["dram_bytes_per_launch"]
+            roof["traffic_source"] = "static ncu capture (%s, %s)" % (os.path.relpath(prof, ROOT), j.get("capture", "profiles/"))
+        except Exception:  # noqa: BLE001
+            pass
+    return roof
+
+
+def bench_secondary(name, dev, steps, cpu_budget_s):
+    """One sub-record per secondary BASELINE config, measured inside the default run at N=1 so that the driver's run
+    times every workload, not only the headline one: value (HBM-resident, CUDA events), roofline, e2e, CPU port."""
+    wl = make_workload(name, 0, dev)
+    wl.to_device()
+    for _ in range(3):
+        wl.kernel_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        wl.kernel_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    h2d = wl.pin()
+    wl.e2e_step()
+    torch.cuda.synchronize()
+    n_e2e = 2
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        out = wl.e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    rec = {"metric": wl.metric, "value": wl.pairs / (ms * 1e-3), "unit": "pairs/s", "steps": steps, "ms_per_step": ms,
+           "dtype": wl.dtype, "config": wl.config(1), "roofline": _roofline(wl, ms, name),
+           "gpu_launches": steps * wl.launches_per_step,
+           "e2e": {"value": wl.pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": out.numel() * out.element_size(), "ms_per_step": e2e_s * 1e3, "note": wl.e2e_note}}
+    if cpu_budget_s > 0:
+        rec["cpu_baseline"] = time_cpu(wl, budget_s=cpu_budget_s, max_reps=10, one_thread_budget_s=0)
+    return rec
 
 
 def main():
@@ -469,9 +647,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="colbert", choices=["colbert", "tk", "knrm", "tkl", "bert_dot"])
+    ap.add_argument("--workload", default="colbert", choices=WORKLOADS)
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: min(steps, 5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the per-workload sub-records (tk, knrm, tkl, bert_dot, ...) of the default N=1 run")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -581,33 +761,16 @@ def main():
     d2h = out.numel() * out.element_size()
 
     if rank == 0:
-        hbm_peak, peak_src = _peaks()
-        if wl.bound == "hbm":
-            achieved = wl.alg_bytes / (kern_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": wl.kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
-                    "algorithmic_bytes_per_launch": wl.alg_bytes, "algorithmic_bytes": wl.alg_note}
-        else:
-            tf_peak, tf_src = _tensor_peak()
-            achieved = wl.flops / (kern_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": wl.kernel, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tf_peak, "traffic": None, "peak_source": tf_src, "kernel_ms": kern_ms,
-                    "algorithmic_flops_per_launch": wl.flops, "algorithmic_flops": wl.alg_note}
         line = {"metric": wl.metric, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(world),
                 "clocks": clocks,
                 "e2e": {"value": pairs_per_step / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "note": wl.e2e_note},
-                "gpu_launches": args.steps * {"tkl": 2, "bert_dot": 3}.get(args.workload, 1),  # tkl: windows + hills; bert_dot: fill, GEMM+top-k, merge
-                "roofline": roof}
-        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
-        prof = os.path.join(ROOT, "profiles", "maxsim_traffic.json" if args.workload == "colbert" else f"{args.workload}_traffic.json")
-        if os.path.isfile(prof):
-            try:
-                line["roofline"]["traffic"] = json.load(open(prof))["dram_bytes_per_launch"]
-            except Exception:
-                pass
+                "gpu_launches": args.steps * wl.launches_per_step,
+                "roofline": _roofline(wl, kern_ms, args.workload)}
+        if hasattr(wl, "h2d_dense"):
+            line["e2e"]["h2d_bytes_dense"] = wl.h2d_dense
         if args.workload == "colbert":
             # informational: same workload with the ragged fetch (padding rows are never read from HBM)
             from matchmaker_b200 import interaction
@@ -623,8 +786,33 @@ def main():
                                     "note": "impl=tcgen05_ragged on the same HBM-resident inputs, 1 GPU: rows past each "
                                             "document's last unmasked token are not fetched (mean 75 of 180 tokens); not "
                                             "used for `value` or the roofline"}
+            if world == 1:
+                # the same public call for a caller that does NOT pin: pageable host tensors, staged slab pipeline
+                wl.e2e_pageable_step()
+                tp = time.perf_counter()
+                wl.e2e_pageable_step()
+                tp = time.perf_counter() - tp
+                line["e2e"]["pageable"] = {"value": wl.pairs / tp, "unit": "pairs/s", "ms_per_step": tp * 1e3,
+                                           "h2d_bytes_per_step": wl.h2d_dense,
+                                           "note": "same call on pageable host tensors: nothing is pinned anywhere, the library "
+                                                   "stages 96 MB slabs (cudaMemcpyAsync from pageable memory), every padded row travels"}
+                del wl.pg
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = time_cpu(wl)
+        if world == 1 and args.workload == "colbert" and not args.no_secondary:
+            # free the headline workload's 3 GB before the secondary ones allocate theirs
+            for a in ("cd", "cdm", "d", "dm", "h", "q32", "d32"):
+                if hasattr(wl, a):
+                    delattr(wl, a)
+            torch.cuda.empty_cache()
+            subs = {}
+            for name in SECONDARY:
+                try:
+                    subs[name] = bench_secondary(name, dev, steps=min(args.steps, 10), cpu_budget_s=0 if args.no_cpu_baseline else 3.0)
+                except Exception as e:  # noqa: BLE001  (a failing secondary workload must not lose the headline line)
+                    subs[name] = {"error": repr(e)}
+                torch.cuda.empty_cache()
+            line["workloads"] = subs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
