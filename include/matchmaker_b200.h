@@ -250,6 +250,20 @@ MMB200_API int mmb200_flat_ip_topk(const void* queries, const void* passages, co
 MMB200_API int mmb200_topk_merge(const float* cand_scores, const int64_t* cand_ids, float* out_scores,
                                  int64_t* out_ids, int64_t nq, int32_t n_candidates, int32_t k, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Storage block loader: byte ranges of files -> one contiguous DEVICE buffer.
+ *
+ * Replaces: the host path of the encoded collection between matchmaker/dense_retrieval.py:291-302
+ *           (np.memmap of token_reps_<n>.npy cut to storage_filled_to_index) and :328
+ *           (indexer.index(id_mapping, storage) -> faiss add_with_ids from host arrays).
+ * Segment s = nbytes[s] bytes of file paths[s] starting at file_offsets[s]; segments land back to back at
+ * dst_device.  pread() into two pinned staging buffers of staging_bytes (0 = 32 MiB) each, cudaMemcpyAsync on
+ * `stream`, read of the next piece overlapped with the transfer of the previous one.  Returns after the last
+ * piece has left the staging buffers (the device copies are complete on `stream` by then).
+ * ------------------------------------------------------------------------------------------ */
+MMB200_API int mmb200_storage_load(const char* const* paths, const int64_t* file_offsets, const int64_t* nbytes,
+                                   int32_t n_segments, void* dst_device, int64_t staging_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,8 @@ from . import interaction
 class _MaxSim(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, d, q_mask, d_mask, docs_per_query):
-        need_grad = q.requires_grad or d.requires_grad
+        # ctx.needs_input_grad is all False under torch.no_grad() / for detached inputs: nothing is saved then
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         if need_grad:
             out, argmax = interaction.maxsim(q, d, q_mask, d_mask, docs_per_query=docs_per_query, return_argmax=True)
             ctx.save_for_backward(q, d, argmax)
@@ -37,7 +38,8 @@ def maxsim(q: torch.Tensor, d: torch.Tensor, q_mask: Optional[torch.Tensor] = No
 class _KernelPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale):
-        need_grad = any(t is not None and t.requires_grad for t in (q, d, weight, alpha))
+        # needs_input_grad (not tensor.requires_grad: parameters always require grad, also under no_grad)
+        need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 6, 7))
         out = interaction.kernel_pool(q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale,
                                       want_per_kernel=True, want_per_kernel_query=need_grad)
         if need_grad:

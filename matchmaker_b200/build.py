@@ -60,14 +60,16 @@ def _all_inputs():
     return sources() + hdrs
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, prof: bool = False) -> str:
+    """prof=True adds -DMMB200_ENABLE_PROF: the MMB200_*_PROF / MMB200_KP_RAW debugging switches (they allocate and
+    synchronise inside the launch path) exist only in such a build, never in the product library."""
     stamp = os.path.join(OBJ_DIR, "stamp.sha256")
-    digest = _digest(_all_inputs())
+    digest = _digest(_all_inputs()) + ("+prof" if prof else "")
     if not force and os.path.isfile(LIB_PATH) and os.path.isfile(stamp) and open(stamp).read() == digest:
         return LIB_PATH
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + (["-DMMB200_ENABLE_PROF"] if prof else [])
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
@@ -95,5 +97,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--prof", action="store_true", help="debugging build with the MMB200_*_PROF switches compiled in")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    print(build(force=a.force, verbose=a.verbose, prof=a.prof))

@@ -692,6 +692,7 @@ extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, co
       return MMB200_OK;
     };
     if (out_params) *out_params = P;
+#ifdef MMB200_ENABLE_PROF
     if (pp.cl == 1 && out_params && getenv("MMB200_FLATIP_PROF")) {  // debugging aid: per-role wait cycles
       long long* prof = nullptr;
       long long h[12] = {0};
@@ -708,6 +709,7 @@ extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, co
               h[4], h[0], h[1], h[2], h[3], h[5], h[6], h[7]);
       return MMB200_OK;
     }
+#endif
     return pp.cl == 1   ? launch(flat_ip_tc_kernel<1, false>)
            : pp.cl == 2 ? launch(flat_ip_tc_kernel<2, false>)
                         : launch(flat_ip_tc_kernel<4, false>);

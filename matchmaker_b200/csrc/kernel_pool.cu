@@ -491,10 +491,7 @@ extern "C" int mmb200_kernel_pool_fwd(const float* q, const float* d, const void
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (impl != MMB200_IMPL_SIMT) {
     bool handled = false;
-    // MMB200_KP_VARIANT=ss selects the first-generation kernel (both MMA operands in shared memory) for A/B runs
-    const char* variant = getenv("MMB200_KP_VARIANT");
-    const bool ss = variant && variant[0] == 's';
-    int rc = ss ? kernel_pool_fwd_tc(P, dev, stream, &handled) : kernel_pool_fwd_ts(P, dev, stream, &handled);
+    int rc = kernel_pool_fwd_ts(P, dev, stream, &handled);
     if (handled) return rc;
     if (impl == MMB200_IMPL_TCGEN05) {
       if (rc == MMB200_OK) { set_error("kernel_pool: shape not supported by the tcgen05 kernel"); rc = MMB200_ERR_UNSUPPORTED; }

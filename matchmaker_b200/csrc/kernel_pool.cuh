@@ -1,5 +1,5 @@
 // Parameter block shared by the kernel-pooling kernels (kernel_pool.cu: FFMA forward/backward;
-// kernel_pool_tc.cu: tcgen05 forward).
+// kernel_pool_ts.cu: tcgen05 forward).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -34,9 +34,8 @@ struct KpParams {
 };
 
 struct DeviceInfo;
-// kernel_pool_tc.cu: *handled = false when the shape is outside the tcgen05 kernel's envelope.
-int kernel_pool_fwd_tc(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, bool* handled);
-// second generation: document operand in tensor memory (kernel_pool_ts.cu); same envelope and outputs
+// tcgen05 forward with the document operand in tensor memory (kernel_pool_ts.cu); *handled = false when the shape is
+// outside the kernel's envelope
 int kernel_pool_fwd_ts(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, bool* handled);
 
 }  // namespace mmb

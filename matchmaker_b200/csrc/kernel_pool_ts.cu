@@ -1,7 +1,7 @@
 // Cosine + RBF kernel pooling forward (KNRM / TK) on the tensor cores with fp32-grade accuracy -- second
 // generation: the document operand of the MMA lives in TENSOR MEMORY.
 //
-// Same arithmetic as kernel_pool_tc.cu (x = hi + lo, hi = x & 0xffffe000, [Qhi;Qlo] stacked along N):
+// Arithmetic (x = hi + lo, hi = x & 0xffffe000, [Qhi;Qlo] stacked along N):
 //
 //     D[128 doc rows x 64] = Dhi[128 x K] * [Qhi; Qlo]^T  +  Dlo[128 x K] * [Qhi; Qlo]^T
 //
@@ -458,14 +458,17 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
   static_assert(8 * KB * 32 <= 2 * 128 * 32, "end-of-pair scratch must fit inside the cosine tiles");
   const size_t fixed = (size_t)(2 * 128 * 32) * sizeof(float) + sizeof(KpShared) + 1024 + (size_t)kOps * kQ64Bytes;
   int n_raw = std::min<int>(kMaxRaw, (int)(((size_t)dev.max_smem_optin - fixed) / kRawBytes));
+#ifdef MMB200_ENABLE_PROF
   if (const char* e = getenv("MMB200_KP_RAW")) n_raw = std::max(2, std::min(n_raw, atoi(e)));
+#endif
   const size_t smem = fixed + (size_t)n_raw * kRawBytes;
   if (n_raw < 2 || smem > (size_t)dev.max_smem_optin) {
     set_error("kernel_pool tcgen05: shared-memory plan does not fit");
     return MMB200_ERR_UNSUPPORTED;
   }
   const int grid = (int)std::min<int64_t>(dev.sm_count, P.B);
-  if (KB == 21 && getenv("MMB200_KP_PROF")) {  // debugging aid: where does each role of CTA 0 wait?
+#ifdef MMB200_ENABLE_PROF  // debugging builds only (python -m matchmaker_b200.build --prof): cudaMalloc + sync in the launch path
+  if (KB == 21 && getenv("MMB200_KP_PROF")) {  // where does each role of CTA 0 wait?
     long long* prof = nullptr;
     long long h[13] = {0};
     MMB_CHECK_CUDA(cudaMalloc(&prof, sizeof(h)));
@@ -481,6 +484,7 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
             h[11], h[0], h[1], h[2], h[3], h[4], h[5], h[12], h[6], h[7], h[8], h[9], h[10]);
     return MMB200_OK;
   }
+#endif
   MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_ts_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel_pool_ts_kernel<KB, false><<<grid, kThreads, smem, stream>>>(tq, td, td_last, P, n_raw, last_box_rows, nullptr);
   MMB_CHECK_CUDA(cudaGetLastError());

@@ -396,6 +396,7 @@ extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int grid = (int)std::min<int64_t>(B * P.segs, (int64_t)dev.sm_count * 2);
+#ifdef MMB200_ENABLE_PROF
   if (KB == 12 && getenv("MMB200_TKL_PROF")) {
     long long* prof = nullptr;
     long long h[5] = {0};
@@ -410,6 +411,7 @@ extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
             h[2], h[3], h[4]);
     return MMB200_OK;
   }
+#endif
   if (KB == 12) {
     MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_window_kernel<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     tkl_window_kernel<12, false><<<grid, kThreads, need, stream>>>(P, nullptr);

@@ -26,9 +26,8 @@ class FlatIPIndexer(BaseNNIndexer):
         if not self.use_gpu:
             raise _lib.MatchmakerB200Error("FlatIPIndexer runs on the GPU only (faiss_use_gpu must be True); "
                                            "there is no CPU fallback")
-        if not self.use_fp16:
-            raise _lib.MatchmakerB200Error("FlatIPIndexer stores passages in fp16 (token_dtype: float16, the reference's "
-                                           "documented setting); fp32 storage is not implemented")
+        # token_dtype float16 -> fp16 storage (faiss useFloat16, faiss_indices.py:65); anything else -> fp32 storage
+        self.store_dtype = torch.float16 if self.use_fp16 else torch.float32
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.group = process_group
         self.passages: Optional[torch.Tensor] = None   # [n_local, dim] fp16 on self.device
@@ -42,25 +41,28 @@ class FlatIPIndexer(BaseNNIndexer):
         return 0, 1
 
     def index(self, ids: List[numpy.ndarray], data_chunks: List[numpy.ndarray]):
-        """ids: list of int64 arrays; data_chunks: list of [n_i, token_dim] arrays (fp16 memmaps in the reference).
-        Every rank is given the same lists and keeps rows shard_bounds(n, rank, world)."""
+        """ids: list of int64 arrays; data_chunks: list of [n_i, token_dim] arrays (the fp16 memmaps of
+        dense_retrieval.py:297-302).  Every rank is given the same lists and keeps rows shard_bounds(n, rank, world).
+        The rows go to HBM through token_storage.blocks_to_device: file-backed memmaps are read by the native loader
+        (pread -> pinned staging -> cudaMemcpyAsync), only the byte range this rank owns is touched."""
+        from .token_storage import blocks_to_device
         rank, world = self._world()
         n = int(sum(len(x) for x in ids))
         lo, hi = sharding.shard_bounds(n, rank, world)
-        id_parts, vec_parts, off = [], [], 0
-        for i_arr, d_arr in zip(ids, data_chunks):
-            a, b = max(lo, off), min(hi, off + len(i_arr))
-            if a < b:
-                id_parts.append(torch.from_numpy(numpy.ascontiguousarray(i_arr[a - off:b - off]).astype(numpy.int64)))
-                vec_parts.append(torch.from_numpy(numpy.ascontiguousarray(d_arr[a - off:b - off])).to(
-                    self.device, dtype=torch.float16, non_blocking=False))
-            off += len(i_arr)
-        self.n_total = n
-        if vec_parts:
-            self.passages = torch.cat(vec_parts, dim=0)
+        self.n_total, self.lo, self.hi = n, lo, hi
+        if hi > lo:
+            with torch.cuda.device(self.device):
+                vecs = blocks_to_device(data_chunks, lo, hi, self.device)
+            self.passages = vecs if vecs.dtype == self.store_dtype else vecs.to(self.store_dtype)
+            id_parts, off = [], 0
+            for i_arr in ids:
+                a, b = max(lo, off), min(hi, off + len(i_arr))
+                if a < b:
+                    id_parts.append(torch.from_numpy(numpy.ascontiguousarray(i_arr[a - off:b - off]).astype(numpy.int64)))
+                off += len(i_arr)
             self.ids = torch.cat(id_parts).to(self.device)
         else:
-            self.passages = torch.empty((0, self.token_dim), dtype=torch.float16, device=self.device)
+            self.passages = torch.empty((0, self.token_dim), dtype=self.store_dtype, device=self.device)
             self.ids = torch.empty(0, dtype=torch.int64, device=self.device)
 
     def search(self, query_vec: numpy.ndarray, top_n: int):
@@ -87,11 +89,29 @@ class FlatIPIndexer(BaseNNIndexer):
             s, i = sharding.all_gather_merge(s, i, top_n, self.group)
         return s, i
 
+    def _shard_path(self, path: str) -> str:
+        rank, world = self._world()
+        return path if world == 1 else f"{path}.rank{rank}of{world}"
+
     def save(self, path: str):
-        torch.save({"passages": self.passages.cpu(), "ids": self.ids.cpu(), "n_total": self.n_total}, path)
+        """dense_retrieval.py calls indexer.save(run_folder/faiss.index) after index().  One file per rank
+        (`<path>.rank<r>of<w>` when the job has more than one rank -- every rank owns a different slab, so they must
+        not write the same file), each recording its row range and the world size it was cut for."""
+        rank, world = self._world()
+        torch.save({"passages": self.passages.cpu(), "ids": self.ids.cpu(), "n_total": self.n_total,
+                    "lo": getattr(self, "lo", 0), "hi": getattr(self, "hi", self.n_total), "world": world, "rank": rank,
+                    "token_dtype": str(self.store_dtype)}, self._shard_path(path))
 
     def load(self, path: str, config_overwrites=None):
-        blob = torch.load(path)
-        self.passages = blob["passages"].to(self.device)
+        rank, world = self._world()
+        blob = torch.load(self._shard_path(path))
+        saved_world, saved_rank = blob.get("world", 1), blob.get("rank", 0)
+        lo, hi = sharding.shard_bounds(blob["n_total"], rank, world)
+        if saved_world != world or saved_rank != rank or (blob.get("lo", lo), blob.get("hi", hi)) != (lo, hi):
+            raise _lib.MatchmakerB200Error(
+                f"index file {self._shard_path(path)} holds rows [{blob.get('lo')},{blob.get('hi')}) of rank {saved_rank} of "
+                f"{saved_world}; this job is rank {rank} of {world} and needs rows [{lo},{hi}) -- re-index or load with the "
+                "same world size")
+        self.passages = blob["passages"].to(self.device, dtype=self.store_dtype)
         self.ids = blob["ids"].to(self.device)
-        self.n_total = blob["n_total"]
+        self.n_total, self.lo, self.hi = blob["n_total"], lo, hi

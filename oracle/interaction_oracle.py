@@ -244,6 +244,75 @@ def flat_ip_search(queries: torch.Tensor, passages: torch.Tensor, ids: torch.Ten
     return best_s, best_i
 
 
+def flat_ip_check_exact(queries: torch.Tensor, passages: torch.Tensor, ids: torch.Tensor, got_scores: torch.Tensor,
+                        got_ids: torch.Tensor, k: int, chunk_q: int = 64) -> dict:
+    """Checker for exact inner-product top-k results against an fp64 ranking.
+
+    The products of fp16 / bf16 values are exact in fp32; what differs between any two fp32 implementations
+    (faiss's cuBLAS tiles, torch's CPU sgemm, our tcgen05 chain) is the ORDER of the dim additions.  The fp64 scores
+    s64 are the arbiter: with ``tol[q,p] = 4 * sqrt(dim/16) * 2^-24 * sum_i |q_i p_i|`` (a random-walk bound on the
+    accumulation error of dim/16 fp32 accumulator updates, x4 margin; the worst case dim * 2^-24 * sum|q_i p_i| is never
+    approached)
+
+      * every returned score must lie within tol of s64 of the returned id;
+      * rank j of query q is DECIDED when s64 separates it from both fp64 neighbours by more than 2*tol: there the
+        returned id must equal the fp64 id, bit-exact;
+      * undecided ranks (fp64 near-ties; exact ties are ordered by id ascending in both) may only hold an id from
+        their own near-tie run, which for the last ranks extends past k.
+
+    Raises AssertionError on any violation; returns counts for the test log."""
+    q64 = queries.double()
+    nq, dim = q64.shape
+    n = passages.shape[0]
+    kk = min(k, n)
+    got_scores, got_ids = got_scores.cpu().double(), got_ids.cpu()
+    margin = min(n, kk + 64)
+    decided = undecided = 0
+    for lo in range(0, nq, chunk_q):
+        hi = min(nq, lo + chunk_q)
+        p64 = passages.double()
+        s = q64[lo:hi] @ p64.T                                        # [c, n] fp64
+        mass = q64[lo:hi].abs() @ p64.abs().T
+        tol = 4.0 * (dim / 16.0) ** 0.5 * 2.0 ** -24 * mass
+        # fp64 ranking under (score desc, id asc)
+        oi = torch.argsort(ids, stable=True)
+        s1, t1 = s[:, oi], tol[:, oi]
+        os_ = torch.argsort(s1, dim=1, descending=True, stable=True)[:, :margin]
+        rs = torch.gather(s1, 1, os_)
+        rt = torch.gather(t1, 1, os_)
+        ri = ids[oi][os_]
+        for r in range(hi - lo):
+            gi, gs = got_ids[lo + r, :kk], got_scores[lo + r, :kk]
+            # scores: look the returned id up in the fp64 ranking (it must be inside the margin)
+            pos = {int(v): j for j, v in enumerate(ri[r].tolist())}
+            gap = (rs[r, :-1] - rs[r, 1:])
+            sep = gap > 2.0 * torch.maximum(rt[r, :-1], rt[r, 1:])    # rank j separated from rank j+1
+            for j in range(kk):
+                g = int(gi[j])
+                assert g in pos, f"query {lo + r} rank {j}: id {g} is not among the fp64 top-{margin}"
+                jj = pos[g]
+                assert abs(gs[j].item() - rs[r, jj].item()) <= rt[r, jj].item(), \
+                    f"query {lo + r} rank {j}: score {gs[j].item()} vs fp64 {rs[r, jj].item()} (tol {rt[r, jj].item():.2e})"
+                left_ok = j == 0 or bool(sep[j - 1])
+                right_ok = j + 1 >= margin or bool(sep[j])
+                if left_ok and right_ok:
+                    decided += 1
+                    assert g == int(ri[r, j]), (f"query {lo + r} rank {j}: id {g} but the fp64 ranking separates id "
+                                                f"{int(ri[r, j])} by more than the accumulation bound")
+                else:
+                    undecided += 1
+                    a = j
+                    while a > 0 and not bool(sep[a - 1]):
+                        a -= 1
+                    b = j
+                    while b + 1 < margin and not bool(sep[b]):
+                        b += 1
+                    assert a <= jj <= b, f"query {lo + r} rank {j}: id {g} (fp64 rank {jj}) outside its near-tie run [{a},{b}]"
+    if n < k:
+        assert (got_ids[:, n:] == -1).all()
+    return {"decided": decided, "undecided": undecided}
+
+
 # ----------------------------------------------------------------------------
 # TKL: chunked kernel activations + sliding-window pooling + top-3 hills
 # ----------------------------------------------------------------------------

@@ -52,7 +52,7 @@ def _check(a, b, what, rtol=1e-6, atol=1e-7):
 
 def golden_knrm():
     torch.manual_seed(100)
-    for tag, (B, Lq, Ld, D, K) in {"small": (4, 8, 24, 32, 11), "cfg1": (2, 30, 60, 300, 11)}.items():
+    for tag, (B, Lq, Ld, D, K) in {"small": (4, 8, 24, 32, 11), "cfg1": (32, 30, 180, 300, 11)}.items():
         ref = R.load_knrm(K)
         q, d, qm, dm = O.synth_kernel_pool_inputs(B, Lq, Ld, D, seed=1235 + Lq)
         with torch.no_grad():
@@ -218,11 +218,11 @@ def main():
     if not R.reference_available():
         print("reference not mounted at", R.REFERENCE_ROOT, "- cannot regenerate golden vectors", file=sys.stderr)
         return 1
-    golden_knrm()
-    golden_tk()
-    golden_tkl()
-    golden_colbert()
-    golden_bert_dot()
+    only = set(sys.argv[1:])   # e.g. `python -m oracle.make_golden knrm` regenerates one family
+    for name, fn in (("knrm", golden_knrm), ("tk", golden_tk), ("tkl", golden_tkl), ("colbert", golden_colbert),
+                     ("bert_dot", golden_bert_dot)):
+        if not only or name in only:
+            fn()
     return 0
 
 

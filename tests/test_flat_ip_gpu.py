@@ -13,21 +13,13 @@ DEV = "cuda"
 
 
 def _check(q, p, ids, k, got_s, got_i):
+    """Scores within 1e-3 relative of the fp32 oracle; ids BIT-EXACT wherever the fp64 ranking separates neighbouring
+    ranks by more than the fp32 accumulation bound (oracle.flat_ip_check_exact states the bound); inside an fp64
+    near-tie run an id may only move within that run."""
     ref_s, ref_i = O.flat_ip_search(q.float(), p, ids, k)
-    got_s, got_i = got_s.cpu(), got_i.cpu()
-    assert_close_rel(got_s, ref_s, what="scores")
-    same = got_i == ref_i
-    if not same.all():
-        # a swap is only acceptable between entries whose scores agree to fp32 accumulation round-off
-        bad = (~same).nonzero()
-        for qi, j in bad.tolist():
-            assert abs(got_s[qi, j].item() - ref_s[qi, j].item()) <= 2e-5 * max(1.0, abs(ref_s[qi, j].item())), \
-                f"query {qi} rank {j}: id {got_i[qi, j]} vs {ref_i[qi, j]} with different scores"
-        assert same.float().mean() > 0.99
-    # as sets the results must agree except for boundary ties
-    for qi in range(q.shape[0]):
-        a, b = set(got_i[qi].tolist()), set(ref_i[qi].tolist())
-        assert len(a ^ b) <= 2
+    assert_close_rel(got_s.cpu(), ref_s, what="scores")
+    stats = O.flat_ip_check_exact(q, p, ids, got_s, got_i, k)
+    assert stats["decided"] >= 0.97 * (stats["decided"] + stats["undecided"]), stats  # the bound must not be vacuous
 
 
 @pytest.mark.parametrize("shape", [(7, 3000, 64, 10), (130, 70000, 128, 100), (64, 20000, 768, 100),
@@ -110,3 +102,35 @@ def test_indexer_dropin_api():
     assert np.array_equal(i1[0], i[0])
     with pytest.raises(_lib.MatchmakerB200Error):
         FlatIPIndexer({"token_dim": 64, "faiss_use_gpu": False, "token_dtype": "float16"})
+
+
+def test_storage_blocks_reach_the_gpu_through_the_native_loader(tmp_path):
+    """Encode folder in the reference's layout -> load_token_storage -> FlatIPIndexer.index: the memmap blocks are read
+    by mmb200_storage_load (pread -> pinned staging -> cudaMemcpyAsync); rows, order and ids must be preserved, also for
+    a row range that starts and ends inside blocks and with a staging buffer smaller than a block."""
+    from matchmaker_b200.retrieval import FlatIPIndexer
+    from matchmaker_b200.retrieval.token_storage import TokenStorageWriter, blocks_to_device, load_token_storage
+    dim, n = 64, 2500
+    q, p = O.synth_dense_inputs(6, n, dim, seed=77)
+    w = TokenStorageWriter(str(tmp_path), token_dim=dim, token_block_size=700, token_dtype="float16")
+    for i in range(n):
+        w.add(f"p{i}", p[i].numpy())
+    w.close()
+    storage, id_mapping, seq_ids, _ = load_token_storage(str(tmp_path), dim, 700, "float16")
+    assert len(storage) == 4 and all(isinstance(s, np.memmap) for s in storage)
+    full = blocks_to_device(storage, 0, n, DEV, staging_bytes=4096 * 3)
+    assert torch.equal(full.cpu(), p)
+    part = blocks_to_device(storage, 650, 1999, DEV, staging_bytes=1 << 20)
+    assert torch.equal(part.cpu(), p[650:1999])
+    mixed = blocks_to_device([storage[0], np.asarray(storage[1]).copy(), storage[2], storage[3]], 100, 2400, DEV)
+    assert torch.equal(mixed.cpu(), p[100:2400])          # an in-memory block between file-backed ones
+    idx = FlatIPIndexer({"token_dim": dim, "faiss_use_gpu": True, "token_dtype": "float16"})
+    idx.index(id_mapping, storage)
+    s, i = idx.search(q.float().numpy(), 10)
+    ref_s, ref_i = O.flat_ip_search(q.float(), p, torch.arange(n), 10)
+    assert np.array_equal(i, ref_i.numpy())
+    idx.save(str(tmp_path / "faiss.index"))
+    idx2 = FlatIPIndexer({"token_dim": dim, "faiss_use_gpu": True, "token_dtype": "float16"})
+    idx2.load(str(tmp_path / "faiss.index"))
+    s2, i2 = idx2.search(q.float().numpy(), 10)
+    assert np.array_equal(i2, i) and np.array_equal(s2, s)

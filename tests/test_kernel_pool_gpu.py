@@ -247,15 +247,10 @@ def test_tcgen05_mask_holes_and_empty_documents():
     dm[3, :128] = 0                                                 # nothing live in the first tile
     qm[4] = 0                                                       # empty query
     ref, sec = O.kernel_pool_tk(q, d, qm, dm, mu, sg, alpha, w)
-    for variant in ("ts", "ss"):
-        os.environ["MMB200_KP_VARIANT"] = variant
-        try:
-            out = interaction.kernel_pool(*_c(q, d, qm, dm, mu, sg, w), alpha=alpha.to(DEV), log_scale=ls,
-                                          want_per_kernel=True, impl="tcgen05")
-        finally:
-            os.environ.pop("MMB200_KP_VARIANT", None)
-        assert_close_rel(out["score"], ref, what=f"score ({variant})")
-        assert_close_rel(out["per_kernel"], sec["per_kernel"], what=f"per_kernel ({variant})")
+    out = interaction.kernel_pool(*_c(q, d, qm, dm, mu, sg, w), alpha=alpha.to(DEV), log_scale=ls,
+                                  want_per_kernel=True, impl="tcgen05")
+    assert_close_rel(out["score"], ref, what="score")
+    assert_close_rel(out["per_kernel"], sec["per_kernel"], what="per_kernel")
 
 
 def test_tcgen05_run_to_run_determinism():

@@ -39,7 +39,7 @@ def _kernels(sass, needle):
     return ks
 
 
-@pytest.mark.parametrize("needle", ["maxsim_qm_kernel", "kernel_pool_ts_kernel", "kernel_pool_tc_kernel", "flat_ip_tc_kernel",
+@pytest.mark.parametrize("needle", ["maxsim_qm_kernel", "kernel_pool_ts_kernel", "flat_ip_tc_kernel",
                                     "maxsim_tc_kernel"])
 def test_tensor_core_kernels_use_tcgen05_and_tma(sass, needle):
     for name, text in _kernels(sass, needle).items():

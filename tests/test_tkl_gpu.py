@@ -82,6 +82,95 @@ def test_seeded_vs_oracle(shape, sat):
     assert_close_rel(score.cpu()[same], ref_score[same], what="score")
 
 
+def _tkl_params(D, g, K=11):
+    return {"mu": torch.tensor([1.0, 0.9, 0.7, 0.5, 0.3, 0.1, -0.1, -0.3, -0.5, -0.7, -0.9]), "sigma": torch.full((K,), 0.1),
+            "dense_weight": torch.randn(K, generator=g) * 0.1, "chunk_scoring": torch.rand(15, generator=g) + 0.5,
+            "sat_emb_reduce1_weight": torch.randn(D, generator=g) * 0.05,
+            "sat_normer_weight": torch.rand(2, generator=g) + 0.5, "sat_normer_bias": torch.randn(2, generator=g) * 0.1,
+            "saturation_linear_weight": torch.randn(2, generator=g) * 0.014, "saturation_linear_bias": torch.tensor([100.0]),
+            "saturation_linear2_weight": torch.randn(2, generator=g) * 0.014, "saturation_linear2_bias": torch.tensor([100.0]),
+            "saturation_linear3_weight": torch.randn(2, generator=g) * 0.014, "saturation_linear3_bias": torch.tensor([100.0]),
+            "kernel_mult0": torch.rand(K, generator=g) + 0.5}
+
+
+@pytest.mark.parametrize("sat", ["embedding", "log"])
+def test_baseline_cfg5_shape_vs_oracle(sat):
+    """BASELINE config 5 token shape (Lq=40, Ld=2000, D=300, 11 kernels), B=20 documents (more than one GPU's share of
+    128/8): MSMARCO-document-shaped lengths so that trailing chunks are dropped by the packing (sigir20_tkl.py:159-162),
+    one full-length document, one shorter than a window, one empty query row pattern.  Window scores within 1e-3, the
+    exact-zero windows exactly zero, the top-3 window ids bit-exact, final score within 1e-3."""
+    B, Lq, Ld, D = 20, 40, 2000, 300
+    g = torch.Generator().manual_seed(555)
+    q = torch.randn(B, Lq, D, generator=g) * 0.4
+    d = torch.randn(B, Ld, D, generator=g) * 0.4
+    q_len = torch.randint(3, Lq + 1, (B,), generator=g)
+    d_len = (torch.randn(B, generator=g) * 500 + 1100).round().clamp(100, Ld).long()
+    d_len[0], d_len[1], d_len[2], d_len[3] = Ld, 17, 40, 1999
+    q_len[0], q_len[4] = Lq, 1
+    qm = (torch.arange(Lq).unsqueeze(0) < q_len.unsqueeze(1)).float()
+    dm = (torch.arange(Ld).unsqueeze(0) < d_len.unsqueeze(1)).float()
+    q, d = q * qm.unsqueeze(-1), d * dm.unsqueeze(-1)
+    for b in range(B):   # exact matches so that the mu = 1.0 kernel fires
+        d[b, int(d_len[b]) // 2] = q[b, 0]
+    cd2, cp2, packed, pieces = O.tkl_chunk_documents(d, dm)
+    assert pieces == 50 and int(packed.sum()) < B * pieces, "the packing must have dropped trailing chunks"
+    chunks = cd2[packed][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous()
+    cmask = cp2[packed][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous()
+    params = _tkl_params(D, g)
+    ref_score, sec = O.tkl_interaction(q, qm, chunks, cmask, packed, pieces, params, sat)
+    gd = {"q_ctx": q, "q_mask": qm, "doc_chunks_ctx": chunks, "doc_chunk_mask": cmask, "packed_indices": packed,
+          "chunk_pieces": torch.tensor(pieces)}
+    ws, (score, orig, top_idx, top15) = _run(gd, params, sat)
+    assert orig.shape == (B, 986)
+    assert_close_rel(orig, sec["orig_score"], what="orig_score")
+    assert ((orig.cpu() == 0) == (sec["orig_score"] == 0)).all(), "exact-zero windows"
+    assert torch.equal(top_idx.cpu(), sec["top_non_overlapping_idx"]), "top-3 window ids must be bit-exact"
+    assert_close_rel(top15, sec["top_k_non_overlapping"], what="top15")
+    assert_close_rel(score, ref_score, what="score")
+    # batch-order independence, bit-exact: a document's windows do not depend on its neighbours or on how the
+    # documents are split over CTAs
+    perm = torch.randperm(B, generator=g)
+    cd2p, cp2p, packedp, _ = O.tkl_chunk_documents(d[perm], dm[perm])
+    gp = {"q_ctx": q[perm], "q_mask": qm[perm], "doc_chunks_ctx": cd2p[packedp][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous(),
+          "doc_chunk_mask": cp2p[packedp][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous(), "packed_indices": packedp,
+          "chunk_pieces": torch.tensor(pieces)}
+    wsp, (scorep, _, top_idxp, _) = _run(gp, params, sat)
+    assert torch.equal(wsp.cpu(), ws.cpu()[perm]) and torch.equal(top_idxp.cpu(), top_idx.cpu()[perm])
+    assert torch.equal(scorep.cpu(), score.cpu()[perm])
+
+
+def test_chunk_holes_and_many_documents():
+    """Non-prefix document masks: an all-padding chunk in the middle of a document is dropped by the packing and must
+    behave as zeros (not as stale data); more documents than SMs; D not a multiple of 32."""
+    B, Lq, Ld, D = 170, 9, 330, 44
+    g = torch.Generator().manual_seed(808)
+    q = torch.randn(B, Lq, D, generator=g) * 0.4
+    d = torch.randn(B, Ld, D, generator=g) * 0.4
+    qm = (torch.arange(Lq).unsqueeze(0) < torch.randint(1, Lq + 1, (B, 1), generator=g)).float()
+    dm = (torch.arange(Ld).unsqueeze(0) < torch.randint(1, Ld + 1, (B, 1), generator=g)).float()
+    dm[0] = 1.0
+    dm[0, 75:130] = 0        # chunk slot 2 (positions 80..119) is entirely padding
+    dm[1] = 1.0
+    dm[1, 0:45] = 0          # leading empty chunk
+    dm[2] = (torch.rand(Ld, generator=g) < 0.5).float()   # holes everywhere
+    dm[3] = 0                # empty document
+    q, d = q * qm.unsqueeze(-1), d * dm.unsqueeze(-1)
+    cd2, cp2, packed, pieces = O.tkl_chunk_documents(d, dm)
+    chunks = cd2[packed][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous()
+    cmask = cp2[packed][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous()
+    params = _tkl_params(D, g)
+    for sat in ("embedding", "log"):
+        ref_score, sec = O.tkl_interaction(q, qm, chunks, cmask, packed, pieces, params, sat)
+        gd = {"q_ctx": q, "q_mask": qm, "doc_chunks_ctx": chunks, "doc_chunk_mask": cmask, "packed_indices": packed,
+              "chunk_pieces": torch.tensor(pieces)}
+        ws, (score, orig, top_idx, top15) = _run(gd, params, sat)
+        assert_close_rel(orig, sec["orig_score"], what=f"orig_score ({sat})")
+        assert ((orig.cpu() == 0) == (sec["orig_score"] == 0)).all()
+        same = (top_idx.cpu() == sec["top_non_overlapping_idx"]).all(dim=1)
+        assert same.float().mean() > 0.97
+        assert_close_rel(score.cpu()[same], ref_score[same], what=f"score ({sat})")
+
+
 def test_dropin_class_matches_reference_golden():
     from matchmaker_b200.rankers.tkl import TKL_sigir20
     for sat in ("embedding", "log"):
