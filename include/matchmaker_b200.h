@@ -188,13 +188,17 @@ MMB200_API int mmb200_dot_pairs(const void* q, const void* d, float* out, int64_
  *                saturation_linear2.weight[2], .bias, saturation_linear3.weight[2], .bias}
  * saturation 1 ("log", :245-246): sat_params[K] = kernel_mult[0]
  * window_score  [B, W] f32 out, W = (C*40 - 30)/2 + 1  (raw dense output, sentinel not yet applied)
+ * n_chunks      Nc (rows of `chunks` / `chunk_mask`)
+ * impl          MMB200_IMPL_AUTO: the TMA + tcgen05 kernel (Lq * K <= 512) when the kernel set activates on every cosine
+ *               in [-1, 1] -- decided on the device, no host sync -- else the FFMA kernel; _TCGEN05 / _SIMT force one.
  * ------------------------------------------------------------------------------------------ */
 MMB200_API int mmb200_tkl_window_scores(const float* q, const void* q_mask, const float* chunks,
                                         const void* chunk_mask, const int32_t* slot_to_packed,
                                         const float* mu, const float* sigma, const float* dense_w,
                                         const float* sat_red_w, const float* sat_params,
-                                        float* window_score, int64_t B, int32_t Lq, int32_t D, int32_t C,
-                                        int32_t K, int32_t saturation, int32_t mask_dtype, void* stream);
+                                        float* window_score, int64_t B, int64_t n_chunks, int32_t Lq, int32_t D,
+                                        int32_t C, int32_t K, int32_t saturation, int32_t mask_dtype, int32_t impl,
+                                        void* stream);
 
 /* window_score [B,W] in/out: on return holds the reference's "orig_score" (exact zeros -> -9900
  * sentinel during selection, written back as 0).  chunk_scoring [15]; top_idx [B,3] int64;

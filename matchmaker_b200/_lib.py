@@ -33,7 +33,7 @@ SIGNATURES = {
     "mmb200_maxsim_fwd_host": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
                                           _i64]),
     "mmb200_kernel_pool_fwd": (_c.c_int, [_vp] * 12 + [_i64, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp]),
-    "mmb200_tkl_window_scores": (_c.c_int, [_vp] * 11 + [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mmb200_tkl_window_scores": (_c.c_int, [_vp] * 11 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mmb200_tkl_bwd": (_c.c_int, [_vp] * 18 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mmb200_tkl_top_hills": (_c.c_int, [_vp] * 5 + [_i64, _i32, _vp]),
     "mmb200_flat_ip_workspace_bytes": (_i64, [_i64, _i64, _i32]),

@@ -18,6 +18,7 @@
 
 #include "host_util.cuh"
 #include "masks.cuh"
+#include "tkl.cuh"
 
 namespace mmb {
 
@@ -33,23 +34,6 @@ constexpr int kZStride = kRing + 1;        // odd strides: the window phase walk
 constexpr int kMaxLq = 40;
 constexpr float kTiny = 1e-13f;
 constexpr float kClamp = 1e-10f;
-
-struct TklParams {
-  const float* q;            // [B, Lq, D] contextualised (masked) query embeddings
-  const void* q_mask;        // [B, Lq]
-  const float* chunks;       // [Nc, 40, D] contextualised packed chunks (overlap removed)
-  const void* chunk_mask;    // [Nc, 40]
-  const int32_t* slot_to_packed;  // [B*C], -1 = chunk slot skipped by the packing (all padding)
-  const float* mu;
-  const float* sigma;
-  const float* dense_w;      // [K]
-  const float* sat_red_w;    // [D]   ("embedding" saturation) or nullptr
-  const float* sat_params;   // embedding: 13 floats (see host); log: kernel_mult0[K]
-  float* window_score;       // [B, W]
-  int64_t B;
-  int32_t Lq, D, C, K, W, mask_dtype, saturation;  // saturation: 0 = embedding, 1 = log
-  int32_t segs, chunks_per_seg;
-};
 
 __device__ __forceinline__ float ex2a(float x) {
   float y;
@@ -169,6 +153,7 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P, long 
   float* pk = sp + 16;                              // [20][KB] per-kernel sums over query rows
   float* T = pk + 20 * KB;                          // [20 windows][40][KB] saturated activations
   const int t = threadIdx.x;
+  if (P.plan && P.plan[0] == 1) return;  // the tcgen05 kernel (tkl_ts.cu) took this call
 
   if (t < KB) {
     const bool ok = t < K;
@@ -358,10 +343,12 @@ __global__ void __launch_bounds__(128) tkl_hills_kernel(float* __restrict__ wind
 extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, const float* chunks, const void* chunk_mask,
                                         const int32_t* slot_to_packed, const float* mu, const float* sigma,
                                         const float* dense_w, const float* sat_red_w, const float* sat_params,
-                                        float* window_score, int64_t B, int32_t Lq, int32_t D, int32_t C, int32_t K,
-                                        int32_t saturation, int32_t mask_dtype, void* stream_) {
+                                        float* window_score, int64_t B, int64_t n_chunks, int32_t Lq, int32_t D,
+                                        int32_t C, int32_t K, int32_t saturation, int32_t mask_dtype, int32_t impl,
+                                        void* stream_) {
   using namespace mmb;
   MMB_REQUIRE(q && chunks && slot_to_packed && mu && sigma && dense_w && sat_params && window_score, "null pointer");
+  MMB_REQUIRE(impl == MMB200_IMPL_AUTO || impl == MMB200_IMPL_SIMT || impl == MMB200_IMPL_TCGEN05, "impl: auto, simt or tcgen05");
   MMB_REQUIRE(B >= 0 && Lq >= 1 && Lq <= kMaxLq, "TKL kernel supports 1 <= Lq <= 40");
   MMB_REQUIRE(D > 0 && D % 4 == 0, "embedding dim must be a multiple of 4");
   MMB_REQUIRE(C >= 1 && K >= 1 && K <= 16, "need C >= 1 and K <= 16");
@@ -378,7 +365,8 @@ extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
   TklParams P{};
   P.q = q; P.q_mask = q_mask; P.chunks = chunks; P.chunk_mask = chunk_mask; P.slot_to_packed = slot_to_packed;
   P.mu = mu; P.sigma = sigma; P.dense_w = dense_w; P.sat_red_w = sat_red_w; P.sat_params = sat_params;
-  P.window_score = window_score; P.B = B; P.Lq = Lq; P.D = D; P.C = C; P.K = K; P.mask_dtype = mask_dtype;
+  P.window_score = window_score; P.B = B; P.n_chunks = n_chunks; P.Lq = Lq; P.D = D; P.C = C; P.K = K;
+  P.mask_dtype = mask_dtype;
   P.saturation = saturation;
   P.W = (C * kChunk - kWindow) / 2 + 1;
   // split long documents over several CTAs when there are fewer documents than SMs
@@ -390,11 +378,29 @@ extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
   const int dp = tkl_row_stride(D);
   const size_t need = ((size_t)2 * kMaxLq * dp + kMaxLq * 41 + (size_t)kMaxLq * (kRing * KB + 1) + kMaxLq * kZStride + 3 * kMaxLq +
                        4 * KB + 16 + 20 * KB + (size_t)20 * kMaxLq * KB) * sizeof(float);
-  if (need > (size_t)dev.max_smem_optin) {
+  const bool ffma_fits = need <= (size_t)dev.max_smem_optin;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // Tensor-core kernel first (tkl_ts.cu).  Its plan kernel decides ON THE DEVICE whether the kernel set lets it run
+  // ("cover", see there); the FFMA kernel below is enqueued as well and returns at once when the plan says the
+  // tensor-core kernel took the call -- no host synchronisation either way.
+  int32_t* plan = nullptr;
+  if (impl != MMB200_IMPL_SIMT) {
+    if (!ffma_fits) P.segs = 0;   // tells the tensor-core kernel that nothing can take over
+    bool handled = false;
+    if (int rc = tkl_window_ts_launch(P, dev, stream, &handled, &plan)) return rc;
+    if (impl == MMB200_IMPL_TCGEN05 && !handled) {
+      set_error("tkl_window_scores: shape outside the tcgen05 kernel's envelope (Lq <= 40, K <= 16, Lq * K <= 512)");
+      return MMB200_ERR_UNSUPPORTED;
+    }
+    if (handled && (impl == MMB200_IMPL_TCGEN05 || !ffma_fits)) {
+      MMB_CHECK_CUDA(cudaFreeAsync(plan, stream));
+      return MMB200_OK;
+    }
+  }
+  if (!ffma_fits) {
     set_error("TKL kernel: embedding dim / kernel count too large for the shared-memory plan (D=300 fits with K <= 12)");
     return MMB200_ERR_UNSUPPORTED;
   }
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int grid = (int)std::min<int64_t>(B * P.segs, (int64_t)dev.sm_count * 2);
 #ifdef MMB200_ENABLE_PROF
   if (KB == 12 && getenv("MMB200_TKL_PROF")) {
@@ -420,6 +426,7 @@ extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
     tkl_window_kernel<16, false><<<grid, kThreads, need, stream>>>(P, nullptr);
   }
   MMB_CHECK_CUDA(cudaGetLastError());
+  if (plan) MMB_CHECK_CUDA(cudaFreeAsync(plan, stream));
   return MMB200_OK;
 }
 

@@ -1,0 +1,686 @@
+// TKL (SIGIR'20) window scores on TMA + tcgen05: the cosine of every (query row, document position) pair comes from
+// the tensor cores with fp32-grade accuracy, the RBF activations, the sliding-window sums, the learned saturation
+// and the dense layer are fused behind it; only [B, W] window scores are written.
+//
+// Reference arithmetic: matchmaker/models/published/sigir20_tkl.py:180-252 (the reference materialises
+// [B, Lq, C*40, K] = 450 MB at BASELINE config 5 and re-reads it 30 times through two unfold reductions).
+//
+// Work decomposition.  A document is C chunk slots of 40 positions; slot c is either a packed chunk
+// (slot_to_packed >= 0) or all padding.  Three slots = one TILE of 120 positions = 60 position pairs = 4 window
+// BLOCKS of 15 pairs.  A window (30 positions, stride 2) is 15 consecutive pairs, so with blocks of 15 pairs every
+// window is a block SUFFIX plus the next block's PREFIX: two running sums per (query row, kernel) instead of 15
+// re-additions, and -- unlike prefix differences -- only additions of non-negative terms, so empty windows stay
+// exactly empty (the -9900 sentinel of sigir20_tkl.py:257 keys on exact zeros).  tkl_plan_kernel counts the tiles of
+// every document that can hold a non-zero window and prefix-sums them on the device; CTA x of the persistent grid
+// takes the x-th equal share of that global tile sequence (documents are split where the share ends; a share that
+// starts inside a document first replays the previous tile's last block -- its "halo" -- to rebuild the suffix sums).
+// Windows outside every share are exactly 0 and come from one cudaMemsetAsync.
+//
+// Per CTA (896 threads = 7 warpgroups, registers re-dealt with setmaxnreg), same operand pipeline as
+// kernel_pool_ts.cu (x = hi + lo with hi = x & 0xffffe000; [Qhi;Qlo] stacked along the UMMA N dimension, the
+// document operand written to TENSOR MEMORY by the convert warps):
+//   warp 0      TMA producer: per 32-column k-chunk up to three [40 x 32] chunk boxes + one [40 x 32] query box
+//   warp 1      tcgen05.mma kind::tf32, M = 128 (120 used), N = 80 = [40 hi | 40 lo], A from TMEM, 3 accumulators
+//   warps 2-3   query convert (hi / lo B operand, query norms)
+//   warps 4-11  document convert, two threads per position (hi / lo straight into TMEM, position norms)
+//   warps 12-27 epilogue.  Phase A: thread = position, 10 query columns per warp: cosine tile to shared memory (masked
+//               positions -> a sentinel whose activations are exactly 0).  Phase B: thread = (query row i, kernel k),
+//               walks the tile's 60 pairs in registers: activation pair sums, block prefix / suffix, window sum,
+//               saturation (per-document table indexed by the window's token count), w_k * T; a 16-value transposed
+//               butterfly per block reduces over the warp, 60 threads add the per-warp partials in a fixed order.
+//
+// The window "length" of sigir20_tkl.py:210 counts positions whose K activations do not all vanish.  When every
+// cosine in [-1, 1] activates at least one kernel (checked on the device by the plan kernel: true for every kernel
+// set the reference ships) that is the count of unmasked positions, which is what this kernel uses; otherwise the
+// plan says so and the FFMA kernel in tkl.cu, which tests the activations themselves, runs instead.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "host_util.cuh"
+#include "masks.cuh"
+#include "ptx.cuh"
+#include "tkl.cuh"
+
+namespace mmb {
+
+namespace {
+
+constexpr int kThreads = 896;
+constexpr int kChunk = 40, kWindow = 30;
+constexpr int kTileSlots = 3, kTileRows = kTileSlots * kChunk;   // 120 positions
+constexpr int kTilePairs = kTileRows / 2;                       // 60
+constexpr int kBlk = 15, kBlocks = kTilePairs / kBlk;           // 4 blocks of 15 pairs
+constexpr int kMaxLq = 40;
+constexpr int kNq = 2 * kMaxLq;           // UMMA N: hi columns 0..39, lo columns 40..79
+constexpr int kMaxRaw = 6;
+constexpr int kOps = 4;
+constexpr int kAcc = 3;
+constexpr int kAccCol0 = kOps * 64;       // TMEM: [0, 256) A ring (4 x (32 hi + 32 lo)), [256, 496) 3 accumulators of 80
+constexpr int kDxBytes = 128 * 128;       // [128 rows][32 fp32], rows 0..119 written
+constexpr int kSlotBytes = kChunk * 128;  // one chunk's 40 rows of a k-chunk
+constexpr int kQxBytes = kMaxLq * 128;
+constexpr int kRawBytes = kDxBytes + kQxBytes;   // 21 KB
+constexpr int kQopBytes = kNq * 128;      // B operand: rows 0-39 Q hi, rows 40-79 Q lo
+constexpr int kEpiWarps = 16, kEpiThreads = kEpiWarps * 32;
+constexpr int kFirstDocWarp = 4, kFirstEpiWarp = 12;
+constexpr int kReleaseArrivals = 8 + 64;
+constexpr int kRegsLight = 56, kRegsConvert = 64, kRegsEpilogue = 80;
+constexpr int kCsStride = 44;             // floats per cosine-tile row (11 16-byte units: conflict-free 16-byte row writes)
+constexpr int kSatStride = 33;            // table row stride (token counts 0..30)
+constexpr float kSentinel = 1.0e6f;
+constexpr float kTinyNorm = 1e-13f;
+constexpr float kClamp = 1e-10f;
+
+struct TsShared {
+  uint64_t raw_full[kMaxRaw];
+  uint64_t raw_empty[kMaxRaw];
+  uint64_t op_full[kOps];
+  uint64_t op_empty[kOps];
+  uint64_t accfull[kAcc];
+  uint64_t accempty[kAcc];
+  uint32_t tmem_base;
+  uint32_t pad;
+  float ss_d[kAcc][2][128];
+  float rs_q[kAcc][kMaxLq];
+  float red[kMaxLq];          // sat_emb_reduce1(q_i)
+  float qm[kMaxLq];
+  float sp[16];
+  int lenw[64];               // token count of the window ending at each pair of the tile
+  float dmring[256];          // unmasked flag of the document's positions, indexed by position & 255
+  float part[kEpiWarps][64];  // per-warp partial window scores
+  float sat1[kMaxLq * kSatStride], sat2[kMaxLq * kSatStride], sat3[kMaxLq * kSatStride];
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void split4(const float4 v, uint32_t* hi, uint32_t* lo) {
+  hi[0] = __float_as_uint(v.x) & 0xffffe000u; lo[0] = __float_as_uint(v.x - __uint_as_float(hi[0]));
+  hi[1] = __float_as_uint(v.y) & 0xffffe000u; lo[1] = __float_as_uint(v.y - __uint_as_float(hi[1]));
+  hi[2] = __float_as_uint(v.z) & 0xffffe000u; lo[2] = __float_as_uint(v.z - __uint_as_float(hi[2]));
+  hi[3] = __float_as_uint(v.w) & 0xffffe000u; lo[3] = __float_as_uint(v.w - __uint_as_float(hi[3]));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// plan: tiles per document (prefix sums) + the "cover" test of the kernel set.  One block.
+// plan[0] = cover, plan[1] = total tiles, plan[2 + b] = tiles before document b (b = 0..B).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) tkl_plan_kernel(const int32_t* __restrict__ slot_to_packed, int64_t B, int C,
+                                                        const float* __restrict__ mu, const float* __restrict__ sigma, int K,
+                                                        int force_cover, int32_t* __restrict__ plan) {
+  __shared__ int sums[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (B + 1023) / 1024;
+  const int64_t b0 = min(B, (int64_t)t * per), b1 = min(B, b0 + per);
+  const int tiles_max = (C + kTileSlots - 1) / kTileSlots;
+  auto tiles_of = [&](int64_t b) {
+    int c_last = -1;
+    for (int c = C - 1; c >= 0; --c)
+      if (slot_to_packed[b * C + c] >= 0) { c_last = c; break; }
+    // windows overlapping a packed chunk end at the latest in slot c_last + 1
+    return c_last < 0 ? 0 : min(tiles_max, (c_last + 1) / kTileSlots + 1);
+  };
+  int local = 0;
+  for (int64_t b = b0; b < b1; ++b) local += tiles_of(b);
+  sums[t] = local;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // inclusive scan
+    const int v = t >= o ? sums[t - o] : 0;
+    __syncthreads();
+    sums[t] += v;
+    __syncthreads();
+  }
+  int run = sums[t] - local;
+  for (int64_t b = b0; b < b1; ++b) {
+    plan[2 + b] = run;
+    run += tiles_of(b);
+  }
+  if (t == 1023) { plan[1] = sums[1023]; plan[2 + B] = sums[1023]; }
+  if (t == 0) {
+    // activation k is non-zero (ex2.approx.ftz) for |c - mu_k| * a_k <= sqrt(126); 11.0 leaves a margin.  Sweep the
+    // union of the intervals over [-1.01, 1.01].
+    float x = -1.01f;
+    bool ok = true;
+    while (x < 1.01f) {
+      float reach = x;
+      for (int k = 0; k < K; ++k) {
+        const float h = 11.0f * sigma[k] / sqrtf(0.5f * 1.4426950408889634f);
+        if (mu[k] - h <= x && mu[k] + h > reach) reach = mu[k] + h;
+      }
+      if (reach <= x) { ok = false; break; }
+      x = reach;
+    }
+    plan[0] = (ok || force_cover == 1) && force_cover != -1 ? 1 : 0;
+  }
+}
+
+// The tiles a CTA walks, identically in every role: [g_begin, g_end) of the global tile sequence, preceded by a halo
+// tile when the share starts inside a document.
+struct TileWalk {
+  const int32_t* pre;   // plan + 2
+  int g, g_end;
+  int b;
+  int t;                // tile inside document b
+  int b_end_tile;       // tiles of document b
+  bool halo;
+  __device__ __forceinline__ bool init(const int32_t* plan, int B, int cta, int ncta) {
+    pre = plan + 2;
+    const int total = plan[1];
+    const int per = (total + ncta - 1) / ncta;
+    g = cta * per;
+    g_end = min(total, g + per);
+    if (g >= g_end) return false;
+    int lo = 0, hi = B - 1;   // last document with pre[b] <= g ...
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (pre[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    b = lo;
+    while (pre[b + 1] <= g) ++b;  // ... that has tiles (documents without tiles repeat the prefix value)
+    t = g - pre[b];
+    b_end_tile = pre[b + 1] - pre[b];
+    halo = t > 0;
+    if (halo) --t;
+    return true;
+  }
+  __device__ __forceinline__ bool valid() const { return halo || g < g_end; }
+  __device__ __forceinline__ void next() {
+    if (halo) { halo = false; ++t; return; }
+    ++g; ++t;
+    if (g < g_end && t == b_end_tile) {
+      ++b;
+      while (pre[b + 1] == pre[b]) ++b;
+      t = 0;
+      b_end_tile = pre[b + 1] - pre[b];
+    }
+  }
+};
+
+template <int SAT>
+__global__ void __launch_bounds__(kThreads, 1)
+tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, TklParams P,
+              int n_raw, int fallback_available) {
+  extern __shared__ uint8_t smem_raw[];
+  if (P.plan[0] != 1) {
+    if (!fallback_available && blockIdx.x == 0 && threadIdx.x == 0) {
+      printf("mmb200 tkl: kernel set does not cover the cosine range and the FFMA kernel cannot run this shape\n");
+      __trap();
+    }
+    return;
+  }
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* qring = smem;                                                    // [kOps][Qhi;Qlo]
+  uint8_t* raws = smem + kOps * kQopBytes;                                  // [n_raw][Dx | Qx]
+  float* cs = reinterpret_cast<float*>(raws + (size_t)n_raw * kRawBytes);   // [120][kCsStride] cosine tile
+  TsShared* S = reinterpret_cast<TsShared*>(cs + kTileRows * kCsStride);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nch = (P.D + 31) / 32;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_q);
+    prefetch_tensormap(&tmap_c);
+    for (int s = 0; s < n_raw; ++s) { mbar_init(&S->raw_full[s], 1); mbar_init(&S->raw_empty[s], kReleaseArrivals); }
+    for (int s = 0; s < kOps; ++s) { mbar_init(&S->op_full[s], kReleaseArrivals); mbar_init(&S->op_empty[s], 1); }
+    for (int s = 0; s < kAcc; ++s) { mbar_init(&S->accfull[s], 1); mbar_init(&S->accempty[s], kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 16) S->sp[threadIdx.x] = (SAT == 0 && threadIdx.x < 13) ? P.sat_params[threadIdx.x] : 0.f;
+  if (warp == 1) tmem_alloc(&S->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = S->tmem_base;
+
+  // every role walks the same tile sequence with its own copy of the iterator (set up inside the role branch, after
+  // setmaxnreg, so that it lives in that role's registers)
+#define TKL_WALK() TileWalk tw; const bool have_work = tw.init(P.plan, (int)P.B, (int)blockIdx.x, (int)gridDim.x)
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    setmaxnreg_dec<kRegsLight>();
+    TKL_WALK();
+    if (lane == 0 && have_work) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (; tw.valid(); tw.next()) {
+        int pk[kTileSlots];
+        int n_present = 0;
+#pragma unroll
+        for (int s = 0; s < kTileSlots; ++s) {
+          const int c = tw.t * kTileSlots + s;
+          pk[s] = (c < P.C && !(tw.halo && s < kTileSlots - 1)) ? P.slot_to_packed[(int64_t)tw.b * P.C + c] : -1;
+          n_present += pk[s] >= 0 ? 1 : 0;
+        }
+        const uint32_t bytes = (uint32_t)(n_present * kSlotBytes + kQxBytes);
+        for (int ck = 0; ck < nch; ++ck) {
+          mbar_wait(&S->raw_empty[stage], phase ^ 1u);
+          uint8_t* st = raws + (size_t)stage * kRawBytes;
+          mbar_arrive_expect_tx(&S->raw_full[stage], bytes);
+#pragma unroll
+          for (int s = 0; s < kTileSlots; ++s)
+            if (pk[s] >= 0) tma_load_3d(&tmap_c, st + s * kSlotBytes, &S->raw_full[stage], ck * 32, 0, pk[s], kEvictFirst);
+          tma_load_3d(&tmap_q, st + kDxBytes, &S->raw_full[stage], ck * 32, 0, (int)tw.b, kEvictLast);
+          if (++stage == n_raw) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    setmaxnreg_dec<kRegsLight>();
+    TKL_WALK();
+    if (have_work) {
+      const uint32_t idesc = make_idesc(kFmtTF32, 128, kNq);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, accphase = 0;
+      for (; tw.valid(); tw.next()) {
+        mbar_wait(&S->accempty[acc], accphase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(kAccCol0 + acc * kNq);
+        for (int ck = 0; ck < nch; ++ck) {
+          const int ksteps = (min(32, P.D - ck * 32) + 7) >> 3;
+          mbar_wait(&S->op_full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t abase = tmem_base + (uint32_t)(stage * 64);
+          const uint64_t b0 = make_sw128_kmajor_desc(smem_u32(qring + (size_t)stage * kQopBytes));
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < ksteps) {
+                const uint64_t bq = b0 + (uint64_t)(k * 2);
+                umma_tf32_ts(tmem_d, abase + (uint32_t)(k * 8), bq, idesc, (uint32_t)((ck | k) != 0));
+                umma_tf32_ts(tmem_d, abase + (uint32_t)(32 + k * 8), bq, idesc, 1u);
+              }
+            }
+            umma_commit(&S->op_empty[stage]);
+            if (ck == nch - 1) umma_commit(&S->accfull[acc]);
+          }
+          __syncwarp();
+          if (++stage == kOps) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == kAcc) { acc = 0; accphase ^= 1u; }
+      }
+    }
+  } else if (warp < 4) {
+    // ------------------------------- query convert ------------------------------
+    // 40 rows x 8 float4 per k-chunk = 320 float4 over 64 threads: thread qt owns 16-byte column c = qt & 7 of rows
+    // (qt >> 3) + 8 j, j = 0..4
+    setmaxnreg_dec<kRegsLight>();
+    TKL_WALK();
+    if (have_work) {
+      const int qt = (warp - 2) * 32 + lane;
+      const int c = qt & 7, r0 = qt >> 3;
+      int rs_ = 0, os_ = 0, acc = 0;
+      uint32_t rphase = 0, ophase = 0;
+      for (; tw.valid(); tw.next()) {
+        float ss[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int ck = 0; ck < nch; ++ck) {
+          mbar_wait(&S->raw_full[rs_], rphase);
+          const uint8_t* xq = raws + (size_t)rs_ * kRawBytes + kDxBytes;
+          float4 x[5];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int row = r0 + 8 * j;
+            x[j] = *reinterpret_cast<const float4*>(xq + row * 128 + ((c ^ (row & 7)) << 4));
+            ss[j] = fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, fmaf(x[j].z, x[j].z, fmaf(x[j].w, x[j].w, ss[j]))));
+          }
+          mbar_wait(&S->op_empty[os_], ophase ^ 1u);
+          uint8_t* qo = qring + (size_t)os_ * kQopBytes;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int row = r0 + 8 * j;
+            uint32_t hi[4], lo[4];
+            split4(x[j], hi, lo);
+            const int off = row * 128 + ((c ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(qo + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(qo + kMaxLq * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          if (ck == nch - 1) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              float v = ss[j];
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              v += __shfl_xor_sync(0xffffffffu, v, 2);
+              v += __shfl_xor_sync(0xffffffffu, v, 4);
+              if (c == 0) S->rs_q[acc][r0 + 8 * j] = 1.0f / (sqrtf(v) + kTinyNorm);
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&S->raw_empty[rs_]);
+          mbar_arrive(&S->op_full[os_]);
+          if (++rs_ == n_raw) { rs_ = 0; rphase ^= 1u; }
+          if (++os_ == kOps) { os_ = 0; ophase ^= 1u; }
+        }
+        if (++acc == kAcc) acc = 0;
+      }
+    }
+  } else if (warp < kFirstEpiWarp) {
+    // ------------------------------- document convert ---------------------------
+    setmaxnreg_dec<kRegsConvert>();
+    TKL_WALK();
+    if (have_work) {
+      const int qd = warp & 3;
+      const int half = (warp - kFirstDocWarp) >> 2;
+      const int row = qd * 32 + lane;
+      const int sw = row & 7;
+      int rs_ = 0, os_ = 0, acc = 0;
+      uint32_t rphase = 0, ophase = 0;
+      for (; tw.valid(); tw.next()) {
+        float4 ss4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ck = 0; ck < nch; ++ck) {
+          const bool active = half == 0 || P.D - ck * 32 > 16;   // these 16 columns hold data (warp-uniform)
+          mbar_wait(&S->raw_full[rs_], rphase);
+          const uint8_t* xrow = raws + (size_t)rs_ * kRawBytes + row * 128;
+          float4 x[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            x[c] = active ? *reinterpret_cast<const float4*>(xrow + (((4 * half + c) ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 v = x[c];
+            ss4.x = fmaf(v.x, v.x, ss4.x); ss4.y = fmaf(v.y, v.y, ss4.y); ss4.z = fmaf(v.z, v.z, ss4.z); ss4.w = fmaf(v.w, v.w, ss4.w);
+          }
+          mbar_wait(&S->op_empty[os_], ophase ^ 1u);
+          tc_fence_after_sync();
+          if (active) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(os_ * 64 + 16 * half);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) split4(x[c], hi + 4 * c, lo + 4 * c);
+            tmem_st_32x32b_x16(taddr, hi);
+            tmem_st_32x32b_x16(taddr + 32, lo);
+            tmem_st_wait();
+          }
+          if (ck == nch - 1) S->ss_d[acc][half][row] = (ss4.x + ss4.y) + (ss4.z + ss4.w);
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&S->raw_empty[rs_]);
+            mbar_arrive(&S->op_full[os_]);
+          }
+          if (++rs_ == n_raw) { rs_ = 0; rphase ^= 1u; }
+          if (++os_ == kOps) { os_ = 0; ophase ^= 1u; }
+        }
+        if (++acc == kAcc) acc = 0;
+      }
+    }
+  } else {
+    // ------------------------------- epilogue ------------------------------------
+    setmaxnreg_inc<kRegsEpilogue>();
+    TKL_WALK();
+    if (have_work) {
+      const int ew = warp - kFirstEpiWarp;       // 0..15
+      const int et = ew * 32 + lane;             // 0..511
+      const int qd = warp & 3;                   // TMEM lane quarter
+      const int cg = ew >> 2;                    // query columns 10 cg .. 10 cg + 9 in phase A
+      const int row = qd * 32 + lane;            // position inside the tile
+      const int dmt = P.chunk_mask ? P.mask_dtype : MMB200_MASK_NONE;
+      const int qmt = P.q_mask ? P.mask_dtype : MMB200_MASK_NONE;
+      const int n_ik = P.Lq * P.K;
+      const int n_act_warps = (n_ik + 31) >> 5;
+      const bool ik_live = et < n_ik;
+      const int qi = ik_live ? et / P.K : 0;     // query row of this thread in phase B
+      const int kk = ik_live ? et - qi * P.K : 0;
+      const float mu_k = P.mu[kk];
+      const float a_k = sqrtf(0.5f * 1.4426950408889634f) / P.sigma[kk];
+      const float w_k = ik_live ? P.dense_w[kk] : 0.f;
+      const float km_k = SAT == 1 ? P.sat_params[kk] : 1.f;
+      float suf[kBlk];
+#pragma unroll
+      for (int r = 0; r < kBlk; ++r) suf[r] = 0.f;
+      int acc_slot = 0;
+      uint32_t accphase = 0;
+      int cur_doc = -1;
+      float qm_i = 0.f;
+
+      for (; tw.valid(); tw.next()) {
+        const int b = tw.b;
+        const int t = tw.t;
+        if (b != cur_doc) {
+          // ---- new document: query mask, sat_emb_reduce1(q_i), saturation table indexed by (query row, token count)
+          cur_doc = b;
+          named_bar_sync(1, kEpiThreads);   // nobody still reads the previous document's table / qm
+          if (et < kMaxLq) S->qm[et] = (et < P.Lq && mask_at(P.q_mask, qmt, (int64_t)b * P.Lq + et)) ? 1.f : 0.f;
+          if (SAT == 0) {
+            for (int i = ew; i < kMaxLq; i += kEpiWarps) {
+              float rd = 0.f;
+              if (i < P.Lq) {
+                const float4* qrow = reinterpret_cast<const float4*>(P.q + ((int64_t)b * P.Lq + i) * P.D);
+                const float4* wr = reinterpret_cast<const float4*>(P.sat_red_w);
+                for (int c4 = lane; c4 < (P.D >> 2); c4 += 32) {
+                  const float4 v = __ldg(qrow + c4), w = __ldg(wr + c4);
+                  rd = fmaf(v.x, w.x, rd); rd = fmaf(v.y, w.y, rd); rd = fmaf(v.z, w.z, rd); rd = fmaf(v.w, w.w, rd);
+                }
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) rd += __shfl_xor_sync(0xffffffffu, rd, o);
+              if (lane == 0) S->red[i] = rd;
+            }
+          }
+          named_bar_sync(1, kEpiThreads);
+          if (SAT == 0) {
+            const float* sp = S->sp;
+            for (int e = et; e < kMaxLq * 31; e += kEpiThreads) {
+              const int i = e / 31, len = e - i * 31;
+              // LayerNorm over the pair (reduce(q_i), len), then three Linear(2,1) (sigir20_tkl.py:224-234); the gate
+              // q_mask[i] * (len > 0) of :248 is folded into sat1 / sat3
+              const float a0 = S->red[i], a1 = (float)len;
+              const float mean = (a0 + a1) * 0.5f;
+              const float d0 = a0 - mean, d1 = a1 - mean;
+              const float rstd = rsqrtf((d0 * d0 + d1 * d1) * 0.5f + 1e-5f);
+              const float y0 = d0 * rstd * sp[0] + sp[2], y1 = d1 * rstd * sp[1] + sp[3];
+              const float gate = (S->qm[i] != 0.f && len > 0) ? 1.f : 0.f;
+              S->sat1[i * kSatStride + len] = (y0 * sp[4] + y1 * sp[5] + sp[6]) * gate;
+              S->sat2[i * kSatStride + len] = 1.0f / (y0 * sp[7] + y1 * sp[8] + sp[9]);
+              S->sat3[i * kSatStride + len] = (y0 * sp[10] + y1 * sp[11] + sp[12]) * gate;
+            }
+          }
+          qm_i = S->qm[qi];   // written before the barrier above
+        }
+
+        // ---- phase A: accumulator -> cosine tile -------------------------------------------------------------
+        uint64_t draw = 0;
+        bool present = false;
+        if (row < kTileRows) {
+          const int c = t * kTileSlots + row / kChunk;
+          const int pk = c < P.C ? P.slot_to_packed[(int64_t)b * P.C + c] : -1;
+          present = pk >= 0;
+          if (present) draw = dmt != MMB200_MASK_NONE ? mask_raw(P.chunk_mask, dmt, (int64_t)pk * kChunk + (row % kChunk)) : 1;
+        }
+        mbar_wait(&S->accfull[acc_slot], accphase);
+        tc_fence_after_sync();
+        {
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(kAccCol0 + acc_slot * kNq + 10 * cg);
+          uint32_t h8[8], h2[2], l8[8], l2[2];
+          tmem_ld_32x32b_x8(taddr, h8);
+          tmem_ld_32x32b_x2(taddr + 8, h2);
+          tmem_ld_32x32b_x8(taddr + kMaxLq, l8);
+          tmem_ld_32x32b_x2(taddr + kMaxLq + 8, l2);
+          tmem_ld_wait();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S->accempty[acc_slot]);
+          const bool valid = present && mask_test(draw, dmt);
+          if (row < kTileRows) {
+            const float rsd = 1.0f / (sqrtf(S->ss_d[acc_slot][0][row] + S->ss_d[acc_slot][1][row]) + kTinyNorm);
+            const float* rq = S->rs_q[acc_slot] + 10 * cg;
+            float v[10];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = valid ? (__uint_as_float(h8[j]) + __uint_as_float(l8[j])) * rsd * rq[j] : kSentinel;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) v[8 + j] = valid ? (__uint_as_float(h2[j]) + __uint_as_float(l2[j])) * rsd * rq[8 + j] : kSentinel;
+            float* dst = cs + row * kCsStride + 10 * cg;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) *reinterpret_cast<float2*>(dst + 2 * j) = make_float2(v[2 * j], v[2 * j + 1]);
+            if (cg == 0) S->dmring[(t * kTileRows + row) & 255] = valid ? 1.f : 0.f;
+          }
+        }
+        if (++acc_slot == kAcc) { acc_slot = 0; accphase ^= 1u; }
+        named_bar_sync(2, kEpiThreads);
+        // ---- token count of the window ending at each pair of this tile (sigir20_tkl.py:210 under "cover") ----
+        if (et < kTilePairs) {
+          const int last = t * kTileRows + 2 * et + 1;   // last position of the window ending at pair et
+          float n = 0.f;
+#pragma unroll 6
+          for (int u = 0; u < kWindow; ++u) {
+            const int pos = last - u;
+            if (pos >= 0) n += S->dmring[pos & 255];
+          }
+          S->lenw[et] = (int)n;
+        }
+        named_bar_sync(3, kEpiThreads);
+        // ---- phase B: activations, block prefix / suffix, windows ------------------------------------------------
+        if (ew < n_act_warps) {
+          const int wbase = t * kTilePairs - (kBlk - 1);      // window index of the tile's pair 0
+          for (int j = tw.halo ? kBlocks - 1 : 0; j < kBlocks; ++j) {
+            float tv[16];
+            float pre = 0.f;
+            const float* cblk = cs + (2 * kBlk * j) * kCsStride + qi;
+#pragma unroll
+            for (int r = 0; r < kBlk; ++r) {
+              const float c0 = cblk[(2 * r) * kCsStride], c1 = cblk[(2 * r + 1) * kCsStride];
+              const float x0 = (c0 - mu_k) * a_k, x1 = (c1 - mu_k) * a_k;
+              const float u = ex2f(-x0 * x0) + ex2f(-x1 * x1);
+              pre = r == 0 ? u : pre + u;
+              const float Ssum = r < kBlk - 1 ? suf[r + 1] + pre : pre;
+              suf[r] = u;   // suf[r] of the previous block was consumed by window r - 1
+              const int w = wbase + kBlk * j + r;
+              float tvv = 0.f;
+              if (!tw.halo && w >= 0 && w < P.W) {   // warp-uniform
+                const int len = S->lenw[kBlk * j + r];
+                if (SAT == 0) {
+                  const int ti = qi * kSatStride + len;
+                  const float pw = ex2f(S->sat2[ti] * lg2f(fmaxf(Ssum, kClamp)));
+                  tvv = w_k * (S->sat1[ti] * pw - S->sat3[ti]);
+                } else {
+                  tvv = (len > 0 && qm_i != 0.f) ? w_k * logf(fmaxf(Ssum * km_k, kClamp)) : 0.f;
+                }
+              }
+              tv[r] = tvv;
+            }
+#pragma unroll
+            for (int r = kBlk - 2; r >= 0; --r) suf[r] += suf[r + 1];
+            if (!tw.halo) {
+              tv[15] = 0.f;
+              // transposed butterfly: 16 values x 32 lanes -> lane l holds the warp total of value l >> 1
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const bool up = (lane & 16) != 0;
+                const float send = up ? tv[jj] : tv[jj + 8];
+                const float keep = up ? tv[jj + 8] : tv[jj];
+                tv[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const bool up = (lane & 8) != 0;
+                const float send = up ? tv[jj] : tv[jj + 4];
+                const float keep = up ? tv[jj + 4] : tv[jj];
+                tv[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const bool up = (lane & 4) != 0;
+                const float send = up ? tv[jj] : tv[jj + 2];
+                const float keep = up ? tv[jj + 2] : tv[jj];
+                tv[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              {
+                const bool up = (lane & 2) != 0;
+                const float send = up ? tv[0] : tv[1];
+                const float keep = up ? tv[1] : tv[0];
+                tv[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+              }
+              tv[0] += __shfl_xor_sync(0xffffffffu, tv[0], 1);
+              const int vi = lane >> 1;   // = 8 b4 + 4 b3 + 2 b2 + b1
+              if (!(lane & 1) && vi < kBlk) S->part[ew][kBlk * j + vi] = tv[0];
+            }
+          }
+        }
+        named_bar_sync(4, kEpiThreads);
+        if (!tw.halo && et < kTilePairs) {
+          const int w = t * kTilePairs - (kBlk - 1) + et;
+          if (w >= 0 && w < P.W) {
+            float s = 0.f;
+            for (int ww = 0; ww < n_act_warps; ++ww) s += S->part[ww][et];
+            P.window_score[(int64_t)b * P.W + w] = s;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+#undef TKL_WALK
+
+}  // namespace
+
+int tkl_window_ts_launch(TklParams& P, const DeviceInfo& dev, cudaStream_t stream, bool* handled, int32_t** plan_out) {
+  *handled = false;
+  *plan_out = nullptr;
+  if (P.Lq > kMaxLq || P.K > 16 || P.Lq * P.K > kEpiThreads || P.D % 4 != 0) return MMB200_OK;
+  if (P.B * (int64_t)P.C >= (1ll << 31) || P.B >= (1ll << 31) - 8) return MMB200_OK;
+  const size_t fixed = (size_t)kOps * kQopBytes + (size_t)kTileRows * kCsStride * sizeof(float) + sizeof(TsShared) + 1024;
+  const int n_raw = std::min<int>(kMaxRaw, (int)(((size_t)dev.max_smem_optin - fixed) / kRawBytes));
+  if (n_raw < 2) return MMB200_OK;
+  const size_t smem = fixed + (size_t)n_raw * kRawBytes;
+  CUtensorMap tq, tc;
+  {
+    const uint64_t dims[3] = {(uint64_t)P.D, (uint64_t)P.Lq, (uint64_t)P.B};
+    const uint64_t strides[2] = {(uint64_t)P.D * 4, (uint64_t)P.Lq * P.D * 4};
+    const uint32_t box[3] = {32, (uint32_t)kMaxLq, 1};
+    if (int rc = encode_tensor_map(&tq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, P.q, dims, strides, box,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+      return rc;
+  }
+  {
+    // the packed chunk count is not part of the C ABI: every index the kernel uses comes from slot_to_packed, so the
+    // outer extent only has to be an upper bound (B * C slots)
+    const uint64_t dims[3] = {(uint64_t)P.D, (uint64_t)kChunk, (uint64_t)(P.n_chunks > 0 ? P.n_chunks : P.B * P.C)};
+    const uint64_t strides[2] = {(uint64_t)P.D * 4, (uint64_t)kChunk * P.D * 4};
+    const uint32_t box[3] = {32, (uint32_t)kChunk, 1};
+    if (int rc = encode_tensor_map(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, P.chunks, dims, strides, box,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
+      return rc;
+  }
+  int32_t* plan = nullptr;
+  MMB_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&plan), (size_t)(P.B + 3) * sizeof(int32_t), stream));
+  int force = 0;
+#ifdef MMB200_ENABLE_PROF
+  if (const char* e = getenv("MMB200_TKL_COVER")) force = atoi(e);  // 1 / -1: force the answer of the cover test
+#endif
+  tkl_plan_kernel<<<1, 1024, 0, stream>>>(P.slot_to_packed, P.B, P.C, P.mu, P.sigma, P.K, force, plan);
+  MMB_CHECK_CUDA(cudaGetLastError());
+  P.plan = plan;
+  *plan_out = plan;
+  MMB_CHECK_CUDA(cudaMemsetAsync(P.window_score, 0, (size_t)P.B * P.W * sizeof(float), stream));
+  const int grid = dev.sm_count;
+  const int fallback = P.segs > 0 ? 1 : 0;
+  if (P.saturation == 0) {
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tkl_ts_kernel<0><<<grid, kThreads, smem, stream>>>(tq, tc, P, n_raw, fallback);
+  } else {
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tkl_ts_kernel<1><<<grid, kThreads, smem, stream>>>(tq, tc, P, n_raw, fallback);
+  }
+  MMB_CHECK_CUDA(cudaGetLastError());
+  *handled = true;
+  return MMB200_OK;
+}
+
+}  // namespace mmb

@@ -265,7 +265,7 @@ TKL_CHUNK, TKL_WINDOW = 40, 30
 def tkl_window_scores(q_ctx: torch.Tensor, q_mask: torch.Tensor, doc_chunks: torch.Tensor, chunk_mask: torch.Tensor,
                       packed_indices: torch.Tensor, chunk_pieces: int, mu: torch.Tensor, sigma: torch.Tensor,
                       dense_weight: torch.Tensor, saturation: str, sat_params: torch.Tensor,
-                      sat_red_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      sat_red_weight: Optional[torch.Tensor] = None, impl: str = "auto") -> torch.Tensor:
     """Window scores [B, W] of the TKL interaction stage (sigir20_tkl.py:180-252).
 
     ``packed_indices`` [B*C] bool is the reference's chunk packing mask (:159); ``doc_chunks`` [Nc,40,D] /
@@ -291,7 +291,8 @@ def tkl_window_scores(q_ctx: torch.Tensor, q_mask: torch.Tensor, doc_chunks: tor
     with torch.cuda.device(dev):
         rc = lib.mmb200_tkl_window_scores(_ptr(q_ctx), _ptr(q_mask), _ptr(doc_chunks), _ptr(chunk_mask),
                                           _ptr(slot_to_packed), _ptr(mu), _ptr(sigma), _ptr(dense_weight), _ptr(red),
-                                          _ptr(sat_params), _ptr(out), B, Lq, D, C, K, sat_code, mcode, _stream(dev))
+                                          _ptr(sat_params), _ptr(out), B, doc_chunks.shape[0], Lq, D, C, K, sat_code, mcode,
+                                          _IMPLS[impl], _stream(dev))
     _lib.check(rc, "mmb200_tkl_window_scores")
     return out
 

@@ -20,20 +20,24 @@ def _sat_args(params, sat):
     return params["kernel_mult0"], None
 
 
-def _run(g, params, sat):
+IMPLS = ["simt", "tcgen05"]   # the FFMA kernel (tkl.cu) and the TMA + tcgen05 kernel (tkl_ts.cu)
+
+
+def _run(g, params, sat, impl="auto"):
     sp, red = _sat_args(params, sat)
     ws = interaction.tkl_window_scores(g["q_ctx"].to(DEV), g["q_mask"].to(DEV), g["doc_chunks_ctx"].to(DEV),
                                        g["doc_chunk_mask"].to(DEV), g["packed_indices"].to(DEV), int(g["chunk_pieces"]),
                                        params["mu"].to(DEV), params["sigma"].to(DEV), params["dense_weight"].to(DEV), sat,
-                                       sp.to(DEV), None if red is None else red.to(DEV))
+                                       sp.to(DEV), None if red is None else red.to(DEV), impl=impl)
     return ws, interaction.tkl_top_hills(ws, params["chunk_scoring"].to(DEV))
 
 
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("sat", ["embedding", "log"])
-def test_golden_tkl(sat):
+def test_golden_tkl(sat, impl):
     g = load_golden(f"tkl_{sat}")
     params = {k[3:]: v for k, v in g.items() if k.startswith("p__")}
-    ws, (score, orig, top_idx, top15) = _run(g, params, sat)
+    ws, (score, orig, top_idx, top15) = _run(g, params, sat, impl)
     assert_close_rel(orig, g["orig_score"], what="orig_score")
     assert torch.equal(top_idx.cpu(), g["top_non_overlapping_idx"]), "top-3 window indices must be bit-exact"
     assert_close_rel(top15, g["top_k_non_overlapping"], what="top15")
@@ -42,9 +46,10 @@ def test_golden_tkl(sat):
     assert ((orig.cpu() == 0) == (g["orig_score"] == 0)).all()
 
 
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("sat", ["embedding", "log"])
-@pytest.mark.parametrize("shape", [(3, 40, 2000, 64), (2, 7, 95, 32), (150, 12, 400, 32)])
-def test_seeded_vs_oracle(shape, sat):
+@pytest.mark.parametrize("shape", [(3, 40, 2000, 64), (2, 7, 95, 32), (150, 12, 400, 32), (1, 5, 20, 16), (4, 32, 121, 300)])
+def test_seeded_vs_oracle(shape, sat, impl):
     B, Lq, Ld, D = shape
     g = torch.Generator().manual_seed(Ld + Lq)
     q = torch.randn(B, Lq, D, generator=g) * 0.4
@@ -70,8 +75,9 @@ def test_seeded_vs_oracle(shape, sat):
     ref_score, sec = O.tkl_interaction(q, qm, chunks, cmask, packed, pieces, params, sat)
     gd = {"q_ctx": q, "q_mask": qm, "doc_chunks_ctx": chunks, "doc_chunk_mask": cmask, "packed_indices": packed,
           "chunk_pieces": torch.tensor(pieces)}
-    ws, (score, orig, top_idx, top15) = _run(gd, params, sat)
+    ws, (score, orig, top_idx, top15) = _run(gd, params, sat, impl)
     assert_close_rel(orig, sec["orig_score"], what="orig_score")
+    assert ((orig.cpu() == 0) == (sec["orig_score"] == 0)).all(), "exact-zero windows"
     same = (top_idx.cpu() == sec["top_non_overlapping_idx"]).all(dim=1)
     # index ties: a different-but-equal-valued window may be picked only if the scores tie within tolerance
     for b in (~same).nonzero().flatten().tolist():
@@ -93,8 +99,9 @@ def _tkl_params(D, g, K=11):
             "kernel_mult0": torch.rand(K, generator=g) + 0.5}
 
 
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("sat", ["embedding", "log"])
-def test_baseline_cfg5_shape_vs_oracle(sat):
+def test_baseline_cfg5_shape_vs_oracle(sat, impl):
     """BASELINE config 5 token shape (Lq=40, Ld=2000, D=300, 11 kernels), B=20 documents (more than one GPU's share of
     128/8): MSMARCO-document-shaped lengths so that trailing chunks are dropped by the packing (sigir20_tkl.py:159-162),
     one full-length document, one shorter than a window, one empty query row pattern.  Window scores within 1e-3, the
@@ -120,7 +127,7 @@ def test_baseline_cfg5_shape_vs_oracle(sat):
     ref_score, sec = O.tkl_interaction(q, qm, chunks, cmask, packed, pieces, params, sat)
     gd = {"q_ctx": q, "q_mask": qm, "doc_chunks_ctx": chunks, "doc_chunk_mask": cmask, "packed_indices": packed,
           "chunk_pieces": torch.tensor(pieces)}
-    ws, (score, orig, top_idx, top15) = _run(gd, params, sat)
+    ws, (score, orig, top_idx, top15) = _run(gd, params, sat, impl)
     assert orig.shape == (B, 986)
     assert_close_rel(orig, sec["orig_score"], what="orig_score")
     assert ((orig.cpu() == 0) == (sec["orig_score"] == 0)).all(), "exact-zero windows"
@@ -134,12 +141,13 @@ def test_baseline_cfg5_shape_vs_oracle(sat):
     gp = {"q_ctx": q[perm], "q_mask": qm[perm], "doc_chunks_ctx": cd2p[packedp][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous(),
           "doc_chunk_mask": cp2p[packedp][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous(), "packed_indices": packedp,
           "chunk_pieces": torch.tensor(pieces)}
-    wsp, (scorep, _, top_idxp, _) = _run(gp, params, sat)
+    wsp, (scorep, _, top_idxp, _) = _run(gp, params, sat, impl)
     assert torch.equal(wsp.cpu(), ws.cpu()[perm]) and torch.equal(top_idxp.cpu(), top_idx.cpu()[perm])
     assert torch.equal(scorep.cpu(), score.cpu()[perm])
 
 
-def test_chunk_holes_and_many_documents():
+@pytest.mark.parametrize("impl", IMPLS)
+def test_chunk_holes_and_many_documents(impl):
     """Non-prefix document masks: an all-padding chunk in the middle of a document is dropped by the packing and must
     behave as zeros (not as stale data); more documents than SMs; D not a multiple of 32."""
     B, Lq, Ld, D = 170, 9, 330, 44
@@ -163,12 +171,40 @@ def test_chunk_holes_and_many_documents():
         ref_score, sec = O.tkl_interaction(q, qm, chunks, cmask, packed, pieces, params, sat)
         gd = {"q_ctx": q, "q_mask": qm, "doc_chunks_ctx": chunks, "doc_chunk_mask": cmask, "packed_indices": packed,
               "chunk_pieces": torch.tensor(pieces)}
-        ws, (score, orig, top_idx, top15) = _run(gd, params, sat)
+        ws, (score, orig, top_idx, top15) = _run(gd, params, sat, impl)
         assert_close_rel(orig, sec["orig_score"], what=f"orig_score ({sat})")
         assert ((orig.cpu() == 0) == (sec["orig_score"] == 0)).all()
         same = (top_idx.cpu() == sec["top_non_overlapping_idx"]).all(dim=1)
         assert same.float().mean() > 0.97
         assert_close_rel(score.cpu()[same], ref_score[same], what=f"score ({sat})")
+
+
+def test_kernel_set_without_cover_takes_the_ffma_kernel():
+    """Narrow kernels that leave parts of [-1, 1] without any activation: the window token count is then NOT the mask
+    count (sigir20_tkl.py:210 tests the activations), the plan kernel detects it on the device and the FFMA kernel,
+    which tests the activations themselves, produces the result; forcing the tcgen05 kernel alone leaves the output of
+    the memset (all zero), which is how the test knows which kernel ran."""
+    B, Lq, Ld, D, K = 3, 6, 200, 32, 3
+    g = torch.Generator().manual_seed(4)
+    q = torch.randn(B, Lq, D, generator=g) * 0.4
+    d = torch.randn(B, Ld, D, generator=g) * 0.4
+    qm, dm = torch.ones(B, Lq), torch.ones(B, Ld)
+    for b in range(B):
+        d[b, 10 + b] = q[b, 0]   # an exact match so that the narrow mu = 1 kernel fires somewhere
+    cd2, cp2, packed, pieces = O.tkl_chunk_documents(d, dm)
+    chunks = cd2[packed][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous()
+    cmask = cp2[packed][:, O.TKL_OVERLAP:-O.TKL_OVERLAP].contiguous()
+    params = _tkl_params(D, g)
+    params.update(mu=torch.tensor([1.0, 0.5, -0.5]), sigma=torch.tensor([0.001, 0.01, 0.01]),
+                  dense_weight=torch.tensor([0.3, -0.2, 0.1]), kernel_mult0=torch.ones(3))
+    ref_score, sec = O.tkl_interaction(q, qm, chunks, cmask, packed, pieces, params, "log")
+    gd = {"q_ctx": q, "q_mask": qm, "doc_chunks_ctx": chunks, "doc_chunk_mask": cmask, "packed_indices": packed,
+          "chunk_pieces": torch.tensor(pieces)}
+    ws, (score, orig, top_idx, top15) = _run(gd, params, "log", "auto")
+    assert_close_rel(orig, sec["orig_score"], what="orig_score")
+    assert ((orig.cpu() == 0) == (sec["orig_score"] == 0)).all()
+    ws_tc, _ = _run(gd, params, "log", "tcgen05")
+    assert (ws_tc == 0).all(), "the tcgen05 kernel must decline a kernel set without cover"
 
 
 def test_dropin_class_matches_reference_golden():
