@@ -333,8 +333,8 @@ class TklWorkload:
     dtype = "f32"
     name = "tkl_window_pool"
     metric = "query-doc pairs scored/sec (TKL chunked kernel pooling + window selection, Ld=2000)"
-    kernel = "tkl_window_kernel"
-    launches_per_step = 2   # window scores + top hills
+    kernel = "tkl_ts_kernel"
+    launches_per_step = 4   # slot map, tile plan, window scores (tcgen05), top hills
 
     def __init__(self, rank, dev, B=128):
         from matchmaker_b200 import synthetic as O

@@ -46,6 +46,7 @@ extern "C" {
 #define MMB200_F16 0
 #define MMB200_BF16 1
 #define MMB200_F32 2
+#define MMB200_F32_SPLIT16 3 /* mmb200_flat_ip_topk only: fp32 vectors held as fp16 hi / lo halves (see there) */
 
 /* element types of mask tensors (nonzero = real token, zero = padding) */
 #define MMB200_MASK_NONE 0
@@ -200,11 +201,15 @@ MMB200_API int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
                                         int32_t C, int32_t K, int32_t saturation, int32_t mask_dtype, int32_t impl,
                                         void* stream);
 
-/* window_score [B,W] in/out: on return holds the reference's "orig_score" (exact zeros -> -9900
- * sentinel during selection, written back as 0).  chunk_scoring [15]; top_idx [B,3] int64;
+/* window_score [B,W] in; orig_score [B,W] out (may be the same buffer): the reference's "orig_score" (exact zeros ->
+ * -9900 sentinel during selection, written back as 0).  chunk_scoring [15]; top_idx [B,3] int64;
  * top15 [B,15] ("top_k_non_overlapping"); score [B]. */
-MMB200_API int mmb200_tkl_top_hills(float* window_score, const float* chunk_scoring, int64_t* top_idx,
-                                    float* top15, float* score, int64_t B, int32_t W, void* stream);
+MMB200_API int mmb200_tkl_top_hills(const float* window_score, float* orig_score, const float* chunk_scoring,
+                                    int64_t* top_idx, float* top15, float* score, int64_t B, int32_t W, void* stream);
+
+/* slot_to_packed [n_slots] int32 from the reference's chunk packing mask `packed_indices` (sigir20_tkl.py:159, one
+ * byte per chunk slot, n_slots = B*C): the packed index of the slot, -1 where the chunk was dropped. */
+MMB200_API int mmb200_tkl_slot_map(const void* packed_mask, int32_t* slot_to_packed, int64_t n_slots, void* stream);
 
 /* Backward of the TKL interaction stage (mmb200_tkl_window_scores + mmb200_tkl_top_hills) for
  * d(loss)/d(score) = grad_score [B]: what autograd derives from sigir20_tkl.py:180-286.  Only the <= 15
@@ -231,11 +236,16 @@ MMB200_API int mmb200_tkl_bwd(const float* q, const void* q_mask, const float* c
  *
  * queries  [nq, dim], passages [n_pass, dim]: fp16 or bf16 (`dtype`), dim % 64 == 0, row-major,
  *          resident on the current device (one shard per GPU); fp32 accumulate on the tensor cores.
+ *          dtype MMB200_F32_SPLIT16 (faiss without useFloat16, faiss_indices.py:65,72: fp32 storage): every fp32
+ *          value x (pre-scaled by a power of two so that |x| < 2^15) is held as hi = fp16(x), lo = fp16(x - hi);
+ *          passages [n_pass, 2*dim] = [hi | lo], queries [nq, 3*dim] = [hi | lo | hi]; the kernel runs 3*dim/64
+ *          k-blocks pairing q_hi.p_hi + q_lo.p_hi + q_hi.p_lo (22 mantissa bits per operand, fp32 accumulate) and
+ *          returns scores in the scaled domain (the caller multiplies by 2^-(sq+sp), exact).
  * ids      [n_pass] int64 user ids (add_with_ids) or NULL: id = id_base + row.
  * out_scores [nq, k] f32 descending; out_ids [nq, k] int64; ties ordered by id ascending (faiss leaves
  *          tie order unspecified); when n_pass < k the tail is (-3.4028235e38, -1) as in faiss.
  * workspace: device scratch of at least mmb200_flat_ip_workspace_bytes(nq, n_pass, k) bytes.
- * 1 <= k <= 256.
+ * 1 <= k <= 1024 (k <= 256: 1024-entry candidate lists per query row; larger k: 2048-entry lists).
  * ------------------------------------------------------------------------------------------ */
 MMB200_API int64_t mmb200_flat_ip_workspace_bytes(int64_t nq, int64_t n_pass, int32_t k);
 /* The work decomposition mmb200_flat_ip_topk uses on a device with `sm_count` SMs (pure host arithmetic, no device
@@ -248,9 +258,11 @@ MMB200_API int mmb200_flat_ip_topk(const void* queries, const void* passages, co
                                    int64_t workspace_bytes, int64_t nq, int64_t n_pass, int32_t dim, int32_t k,
                                    int32_t dtype, int64_t id_base, void* stream);
 
-/* Merge candidate lists: cand_scores / cand_ids [nq, n_candidates] (entries with id < 0 or score -inf
- * are ignored) -> the k best per query under (score desc, id asc).  Used after the NCCL all-gather of
- * per-rank top-k lists (the reference merges faiss IndexShards results on the host). */
+/* Merge candidate lists: cand_scores / cand_ids [nq, n_candidates] -> the k best per query under (score desc,
+ * id asc).  A candidate is void when its SCORE is NaN, -inf or -FLT_MAX (faiss's "no result"); ids may be any int64,
+ * negative user ids included (faiss IndexIDMap allows them).  Any n_candidates: more than 8192 per query are merged
+ * in passes.  Used after the NCCL all-gather of per-rank top-k lists (the reference merges faiss IndexShards results on
+ * the host). */
 MMB200_API int mmb200_topk_merge(const float* cand_scores, const int64_t* cand_ids, float* out_scores,
                                  int64_t* out_ids, int64_t nq, int32_t n_candidates, int32_t k, void* stream);
 

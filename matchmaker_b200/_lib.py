@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmatchmaker_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
-F16, BF16, F32 = 0, 1, 2
+F16, BF16, F32, F32_SPLIT16 = 0, 1, 2, 3
 MASK_NONE, MASK_U8, MASK_I32, MASK_I64, MASK_F32 = 0, 1, 2, 3, 4
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_TCGEN05_DOCM, IMPL_TCGEN05_RAGGED = 0, 1, 2, 3, 4
 
@@ -35,7 +35,8 @@ SIGNATURES = {
     "mmb200_kernel_pool_fwd": (_c.c_int, [_vp] * 12 + [_i64, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp]),
     "mmb200_tkl_window_scores": (_c.c_int, [_vp] * 11 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mmb200_tkl_bwd": (_c.c_int, [_vp] * 18 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "mmb200_tkl_top_hills": (_c.c_int, [_vp] * 5 + [_i64, _i32, _vp]),
+    "mmb200_tkl_top_hills": (_c.c_int, [_vp] * 6 + [_i64, _i32, _vp]),
+    "mmb200_tkl_slot_map": (_c.c_int, [_vp, _vp, _i64, _vp]),
     "mmb200_flat_ip_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "mmb200_flat_ip_plan": (_c.c_int, [_i64, _i64, _i32, _i32, _c.POINTER(_i32)]),
     "mmb200_flat_ip_topk": (_c.c_int, [_vp] * 6 + [_i64, _i64, _i64, _i32, _i32, _i32, _i64, _vp]),

@@ -42,8 +42,9 @@ namespace {
 
 constexpr int kEpiPerQuarter = 2;        // epilogue warps per TMEM lane quarter (column halves of a tile, ONE list per row)
 constexpr int kThreads = 64 + 128 * kEpiPerQuarter;  // TMA warp, MMA warp, 8 epilogue warps
-constexpr int kEPL = 32;                 // list entries per lane in a compaction -> capacity 1024 per row
-constexpr int kCap = 32 * kEPL;
+// list entries per lane in a compaction: EPL = 32 -> capacity 1024 per row (k <= 256), EPL = 64 -> 2048 (k <= 1024)
+constexpr int kMaxK = 1024;
+__host__ __device__ constexpr int epl_for_k(int k) { return k <= 256 ? 32 : 64; }
 constexpr int BM = 128;                 // queries per block (UMMA M)
 constexpr int BN = 256;                 // passages per tile (UMMA N)
 constexpr int kABytes = BM * 128;       // one k-block (64 halfs) of the query tile
@@ -68,7 +69,8 @@ struct FipParams {
   const int64_t* ids;       // [n_pass] user ids or nullptr (id = id_base + position)
   int64_t id_base;
   int64_t nq, n_pass;
-  int32_t dim, k, kpad;             // kpad = k rounded up to 32 (list capacity per row is the constant kCap)
+  int32_t dim, k, kpad;             // kpad = k rounded up to 32 (list capacity per row is 32 * EPL)
+  int32_t kblocks, kb_wrap;         // k-blocks of 64 along the QUERY rows; passage k-block = kb < kb_wrap ? kb : kb - kb_wrap
   int32_t n_qblocks, n_ranges, tiles_per_range, n_tiles;
   int32_t fmt;
   uint2* lists;             // [grid][BM][cap]  (score bits, position)
@@ -92,12 +94,12 @@ __device__ __forceinline__ int64_t pos_to_id(const FipParams& P, uint32_t pos) {
 }
 
 // Warp-cooperative compaction of one row's candidate list to its top-k under (score desc, id asc).
-// `list` has `cnt` valid entries (cnt <= kCap = 32 * kEPL).  Returns the new count (min(cnt, k)) and the key of
+// `list` has `cnt` valid entries (cnt <= 32 * EPL).  Returns the new count (min(cnt, k)) and the key of
 // the k-th best entry in *kth_key (kKeyNegInf if fewer than k entries).
 // __noinline__: the epilogue's per-tile loop has to stay inside the instruction cache.  With this routine inlined (and
 // the column loop unrolled) the loop body streamed ~100 KB of code per tile and ran at IPC 0.03.
+template <int EPL>
 __device__ __noinline__ int compact_row(const FipParams& P, uint2* list, int cnt, int lane, uint32_t* kth_key) {
-  constexpr int EPL = kEPL;
   uint32_t key[EPL], pos[EPL];
 #pragma unroll
   for (int j = 0; j < EPL; ++j) {
@@ -142,23 +144,23 @@ __device__ __noinline__ int compact_row(const FipParams& P, uint2* list, int cnt
   c_gt = __reduce_add_sync(0xffffffffu, c_gt);
   c_eq = __reduce_add_sync(0xffffffffu, c_eq);
   int need = P.k - c_gt;  // how many of the entries tied at T survive (1 <= need <= c_eq)
-  uint32_t keep = 0u;     // bit j: entry j of this lane survives
+  uint64_t keep = 0u;     // bit j: entry j of this lane survives
 #pragma unroll
   for (int j = 0; j < EPL; ++j)
-    if (key[j] > T) keep |= 1u << j;
+    if (key[j] > T) keep |= 1ull << j;
   if (need == c_eq) {
 #pragma unroll
     for (int j = 0; j < EPL; ++j)
-      if (key[j] == T) keep |= 1u << j;
+      if (key[j] == T) keep |= 1ull << j;
   } else {
     // rare: more ties than room -> take the `need` smallest ids among them
-    uint32_t taken = 0u;
+    uint64_t taken = 0u;
     for (int n = 0; n < need; ++n) {
       unsigned long long best = ~0ull;
       int bj = -1;
 #pragma unroll
       for (int j = 0; j < EPL; ++j)
-        if (key[j] == T && !(taken & (1u << j))) {
+        if (key[j] == T && !(taken & (1ull << j))) {
           const unsigned long long id = (unsigned long long)(pos_to_id(P, pos[j]) ^ (1ll << 63));  // signed order
           if (id < best) { best = id; bj = j; }
         }
@@ -169,13 +171,13 @@ __device__ __noinline__ int compact_row(const FipParams& P, uint2* list, int cnt
         wbest = ot < wbest ? ot : wbest;
       }
       const unsigned owner = __ballot_sync(0xffffffffu, best == wbest && bj >= 0);
-      if (bj >= 0 && best == wbest && (int)(__ffs(owner) - 1) == lane) { taken |= 1u << bj; keep |= 1u << bj; }
+      if (bj >= 0 && best == wbest && (int)(__ffs(owner) - 1) == lane) { taken |= 1ull << bj; keep |= 1ull << bj; }
     }
   }
   int base = 0;
 #pragma unroll
   for (int j = 0; j < EPL; ++j) {
-    const bool kp = (keep >> j) & 1u;
+    const bool kp = (keep >> j) & 1ull;
     const unsigned b = __ballot_sync(0xffffffffu, kp);
     if (kp) list[base + __popc(b & ((1u << lane) - 1u))] = make_uint2(__float_as_uint(key2f(key[j])), pos[j]);
     base += __popc(b);
@@ -201,7 +203,7 @@ __device__ __noinline__ int compact_row(const FipParams& P, uint2* list, int cnt
     }                                                         \
   } while (0)
 
-template <int CL, bool PROF = false>
+template <int CL, bool PROF = false, int EPL = 32>
 __global__ void __launch_bounds__(kThreads, 1)
 flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_p, FipParams P,
                   long long* prof = nullptr) {
@@ -212,8 +214,9 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   // compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   FipShared* S = reinterpret_cast<FipShared*>(smem + (size_t)kStages * kStageBytes);
+  constexpr int kCap = 32 * EPL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks = P.dim / 64;
+  const int kblocks = P.kblocks;
   const int n_qgroups = (P.n_qblocks + CL - 1) / CL;   // CL consecutive query blocks per cluster work item
   const int n_items = n_qgroups * P.n_ranges;
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
@@ -248,11 +251,12 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             uint8_t* st = smem + (size_t)stage * kStageBytes;
             if (elect_one_sync()) {
               mbar_arrive_expect_tx(&S->full[stage], (uint32_t)kStageBytes);
+              const int kbp = kb < P.kb_wrap ? kb : kb - P.kb_wrap;   // fp32-split storage: [q_hi|q_lo|q_hi] x [p_hi|p_hi|p_lo]
               tma_load_2d(&tmap_q, st, &S->full[stage], kb * 64, qb * BM, kEvictLast);
               if (CL == 1)
-                tma_load_2d(&tmap_p, st + kABytes, &S->full[stage], kb * 64, t * BN, kEvictFirst);
+                tma_load_2d(&tmap_p, st + kABytes, &S->full[stage], kbp * 64, t * BN, kEvictFirst);
               else  // this CTA's slice of the passage tile, written into every CTA of the cluster
-                tma_load_2d_multicast(&tmap_p, st + kABytes + rank * (kBBytes / CL), &S->full[stage], kb * 64,
+                tma_load_2d_multicast(&tmap_p, st + kABytes + rank * (kBBytes / CL), &S->full[stage], kbp * 64,
                                       t * BN + rank * (BN / CL), kAllCtas, kEvictFirst);
             }
             __syncwarp();
@@ -335,7 +339,7 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             if ((idx & 1) != half) continue;
             const int rr = __ffs(m) - 1;
             uint32_t kth;
-            const int nc = compact_row(P, warp_lists + (size_t)rr * kCap, cnt_s[rr], lane, &kth);
+            const int nc = compact_row<EPL>(P, warp_lists + (size_t)rr * kCap, cnt_s[rr], lane, &kth);
             __syncwarp();
             if (lane == 0) {
               cnt_s[rr] = nc;
@@ -417,7 +421,7 @@ flat_ip_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       named_bar_sync(pair_bar, 64);
       for (int rr = half; rr < 32; rr += 2) {
         uint32_t kth;
-        const int nc = compact_row(P, warp_lists + (size_t)rr * kCap, cnt_s[rr], lane, &kth);
+        const int nc = compact_row<EPL>(P, warp_lists + (size_t)rr * kCap, cnt_s[rr], lane, &kth);
         const int64_t qq = (int64_t)qb * BM + quarter * 32 + rr;
         if (qq < P.nq) {
           if (lane == 0 && nc == P.k) atomicMax(P.tau_glob + qq, kth);
@@ -471,20 +475,27 @@ __device__ __forceinline__ bool cand_before(const Cand& a, const Cand& b) {
   return a.id < b.id;
 }
 
+// Block (q, grp) sorts candidates [grp * seg, min(L, (grp + 1) * seg)) of query q and writes its k best to row
+// q * n_groups + grp of the output.  A candidate is void when its score is NaN, -inf or faiss's "no result" value
+// (-FLT_MAX) -- NOT by the sign of its id: faiss IndexIDMap accepts negative user ids.  `final_pass` selects the
+// filler for missing results: (-FLT_MAX, -1) as faiss returns them, or (-inf, -1) between passes.
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ cand_scores,
-                                                         const int64_t* __restrict__ cand_ids, int64_t nq, int L,
-                                                         int Lpow2, int k, float* __restrict__ out_scores,
-                                                         int64_t* __restrict__ out_ids) {
+                                                         const int64_t* __restrict__ cand_ids, int64_t nq, int L, int seg,
+                                                         int n_groups, int Lpow2, int k, int final_pass,
+                                                         float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
   extern __shared__ __align__(16) uint8_t msm[];
   Cand* c = reinterpret_cast<Cand*>(msm);
-  for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
+  for (int64_t item = blockIdx.x; item < nq * n_groups; item += gridDim.x) {
+    const int64_t q = item / n_groups;
+    const int grp = (int)(item % n_groups);
+    const int lo = grp * seg, n = min(seg, L - lo);
     __syncthreads();
     for (int e = threadIdx.x; e < Lpow2; e += blockDim.x) {
       Cand v;
-      if (e < L) {
-        v.s = cand_scores[q * L + e];
-        v.id = cand_ids[q * L + e];
-        v.valid = (v.id >= 0 && v.s == v.s && v.s != -INFINITY) ? 1 : 0;
+      if (e < n) {
+        v.s = cand_scores[q * L + lo + e];
+        v.id = cand_ids[q * L + lo + e];
+        v.valid = (v.s == v.s && v.s > -3.4028234663852886e38f) ? 1 : 0;
       } else {
         v.s = -INFINITY; v.id = -1; v.valid = 0;
       }
@@ -506,8 +517,8 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
     }
     for (int e = threadIdx.x; e < k; e += blockDim.x) {
       const bool ok = e < Lpow2 && c[e].valid;
-      out_scores[q * k + e] = ok ? c[e].s : -3.4028234663852886e38f;  // faiss's "no result" convention
-      out_ids[q * k + e] = ok ? c[e].id : -1;
+      out_scores[item * k + e] = ok ? c[e].s : (final_pass ? -3.4028234663852886e38f : -INFINITY);
+      out_ids[item * k + e] = ok ? c[e].id : -1;
     }
   }
 }
@@ -559,35 +570,80 @@ Plan make_plan(int64_t nq, int64_t n_pass, int k, int sm_count) {
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
-size_t workspace_bytes(const Plan& pl, int64_t nq) {
-  return align256((size_t)nq * sizeof(uint32_t)) + align256((size_t)pl.grid * BM * kCap * sizeof(uint2)) +
+size_t workspace_bytes(const Plan& pl, int64_t nq, int k) {
+  const size_t cap = 32 * (size_t)epl_for_k(k);
+  return align256((size_t)nq * sizeof(uint32_t)) + align256((size_t)pl.grid * BM * cap * sizeof(uint2)) +
          align256((size_t)nq * pl.n_ranges * pl.kpad * sizeof(float)) +
          align256((size_t)nq * pl.n_ranges * pl.kpad * sizeof(int64_t));
 }
 
 size_t total_workspace_bytes(int64_t nq, int64_t n_pass, int k, int sm_count) {
-  return workspace_bytes(make_plan(nq, n_pass, k, sm_count), nq);
+  return workspace_bytes(make_plan(nq, n_pass, k, sm_count), nq, k);
 }
 
 __global__ void fill_u32(uint32_t* p, int64_t n, uint32_t v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// Largest candidate count one shared-memory sort takes (16 B per candidate).  More than that -- many passage ranges at
+// k = 1024, or sharding.topk_all_gather_merge over a shard with thousands of local scores per query -- is merged in
+// passes: groups of kMergeSeg candidates are cut to their k best, the survivors merged again.
+constexpr int kMergeSeg = 8192;
+
 int launch_merge(const float* cand_scores, const int64_t* cand_ids, int64_t nq, int L, int k, float* out_scores,
                  int64_t* out_ids, const DeviceInfo& dev, cudaStream_t stream) {
-  int lp = 1;
-  while (lp < L) lp <<= 1;
-  lp = std::max(lp, 2);
-  const size_t smem = (size_t)lp * sizeof(Cand);
-  if (smem > (size_t)dev.max_smem_optin) {
-    set_error("topk merge: too many candidates per query for one shared-memory sort (" + std::to_string(L) + ")");
-    return MMB200_ERR_UNSUPPORTED;
+  MMB_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kMergeSeg * sizeof(Cand))));
+  const float* in_s = cand_scores;
+  const int64_t* in_i = cand_ids;
+  float* tmp_s[2] = {nullptr, nullptr};
+  int64_t* tmp_i[2] = {nullptr, nullptr};
+  int cur = 0;
+  int rc = MMB200_OK;
+  while (true) {
+    const bool last = L <= kMergeSeg;
+    const int seg = last ? L : kMergeSeg;
+    const int groups = (L + seg - 1) / seg;
+    int lp = 2;
+    while (lp < seg) lp <<= 1;
+    const int k_out = last ? k : std::min(k, seg);
+    float* o_s = out_scores;
+    int64_t* o_i = out_ids;
+    if (!last) {
+      if (cudaMallocAsync(reinterpret_cast<void**>(&tmp_s[cur]), (size_t)nq * groups * k_out * sizeof(float), stream) != cudaSuccess ||
+          cudaMallocAsync(reinterpret_cast<void**>(&tmp_i[cur]), (size_t)nq * groups * k_out * sizeof(int64_t), stream) != cudaSuccess) {
+        set_error("topk merge: cannot allocate the intermediate candidate lists");
+        rc = MMB200_ERR_CUDA;
+        break;
+      }
+      o_s = tmp_s[cur];
+      o_i = tmp_i[cur];
+    }
+    const int grid = (int)std::min<int64_t>(nq * groups, (int64_t)dev.sm_count * 4);
+    topk_merge_kernel<<<grid, 256, (size_t)lp * sizeof(Cand), stream>>>(in_s, in_i, nq, L, seg, groups, lp, k_out, last ? 1 : 0,
+                                                                        o_s, o_i);
+    if (cudaGetLastError() != cudaSuccess) {
+      set_error("topk merge: kernel launch failed");
+      rc = MMB200_ERR_CUDA;
+      break;
+    }
+    if (last) break;
+    in_s = o_s;
+    in_i = o_i;
+    L = groups * k_out;
+    cur ^= 1;
+    if (tmp_s[cur]) {  // the buffers of two passes ago are no longer read by anything enqueued after this point
+      cudaFreeAsync(tmp_s[cur], stream);
+      cudaFreeAsync(tmp_i[cur], stream);
+      tmp_s[cur] = nullptr;
+      tmp_i[cur] = nullptr;
+    }
   }
-  MMB_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)std::min<int64_t>(nq, (int64_t)dev.sm_count * 4);
-  topk_merge_kernel<<<grid, 256, smem, stream>>>(cand_scores, cand_ids, nq, L, lp, k, out_scores, out_ids);
-  MMB_CHECK_CUDA(cudaGetLastError());
-  return MMB200_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (tmp_s[i]) cudaFreeAsync(tmp_s[i], stream);
+    if (tmp_i[i]) cudaFreeAsync(tmp_i[i], stream);
+  }
+  return rc;
 }
 
 }  // namespace
@@ -596,7 +652,7 @@ int launch_merge(const float* cand_scores, const int64_t* cand_ids, int64_t nq, 
 
 extern "C" int64_t mmb200_flat_ip_workspace_bytes(int64_t nq, int64_t n_pass, int32_t k) {
   using namespace mmb;
-  if (nq <= 0 || n_pass <= 0 || k <= 0 || k > 256) return 0;
+  if (nq <= 0 || n_pass <= 0 || k <= 0 || k > kMaxK) return 0;
   DeviceInfo dev;
   if (current_device_info(&dev)) return -1;
   return (int64_t)total_workspace_bytes(nq, n_pass, k, dev.sm_count);
@@ -605,10 +661,10 @@ extern "C" int64_t mmb200_flat_ip_workspace_bytes(int64_t nq, int64_t n_pass, in
 extern "C" int mmb200_flat_ip_plan(int64_t nq, int64_t n_pass, int32_t k, int32_t sm_count, int32_t out[8]) {
   using namespace mmb;
   MMB_REQUIRE(out != nullptr, "null pointer");
-  MMB_REQUIRE(nq > 0 && n_pass > 0 && k >= 1 && k <= 256 && sm_count >= 1, "bad sizes");
+  MMB_REQUIRE(nq > 0 && n_pass > 0 && k >= 1 && k <= kMaxK && sm_count >= 1, "bad sizes");
   MMB_REQUIRE(n_pass < (1ll << 32) - 512, "at most 2^32 passages per shard");
   const Plan pl = make_plan(nq, n_pass, k, sm_count);
-  const uint64_t ws = (uint64_t)workspace_bytes(pl, nq);
+  const uint64_t ws = (uint64_t)workspace_bytes(pl, nq, k);
   out[0] = pl.n_qblocks; out[1] = pl.n_tiles; out[2] = pl.n_ranges; out[3] = pl.tiles_per_range; out[4] = pl.grid; out[5] = pl.cl;
   out[6] = (int32_t)(uint32_t)(ws & 0xffffffffu); out[7] = (int32_t)(uint32_t)(ws >> 32);
   return MMB200_OK;
@@ -621,8 +677,10 @@ extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, co
   using namespace mmb;
   MMB_REQUIRE(queries && passages && out_scores && out_ids && workspace, "null pointer");
   MMB_REQUIRE(nq > 0 && n_pass > 0, "need at least one query and one passage");
-  MMB_REQUIRE(k >= 1 && k <= 256, "fused top-k supports 1 <= k <= 256");
-  MMB_REQUIRE(dtype == MMB200_F16 || dtype == MMB200_BF16, "passage storage must be fp16 or bf16 (faiss useFloat16)");
+  MMB_REQUIRE(k >= 1 && k <= kMaxK, "fused top-k supports 1 <= k <= 1024");
+  MMB_REQUIRE(dtype == MMB200_F16 || dtype == MMB200_BF16 || dtype == MMB200_F32_SPLIT16,
+              "passage storage must be fp16, bf16 or the fp16 hi/lo split of fp32 (MMB200_F32_SPLIT16)");
+  const bool split = dtype == MMB200_F32_SPLIT16;
   MMB_REQUIRE(dim % 64 == 0 && dim >= 64, "vector dim must be a multiple of 64");
   MMB_REQUIRE(n_pass < (1ll << 32) - 512, "at most 2^32 passages per shard");
   MMB_REQUIRE(((reinterpret_cast<uintptr_t>(queries) | reinterpret_cast<uintptr_t>(passages)) & 15) == 0, "16-byte alignment");
@@ -636,11 +694,12 @@ extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, co
   const Plan pl = make_plan(nq, n_pass, k, dev.sm_count);
   MMB_REQUIRE((size_t)workspace_bytes_given >= total_workspace_bytes(nq, n_pass, k, dev.sm_count),
               "workspace too small (see mmb200_flat_ip_workspace_bytes)");
-  const CUtensorMapDataType tdt = dtype == MMB200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType tdt = dtype == MMB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const uint64_t q_cols = split ? 3ull * dim : (uint64_t)dim, p_cols = split ? 2ull * dim : (uint64_t)dim;
   CUtensorMap tq;
   {
-    const uint64_t dims[2] = {(uint64_t)dim, (uint64_t)nq};
-    const uint64_t strides[1] = {(uint64_t)dim * 2};
+    const uint64_t dims[2] = {q_cols, (uint64_t)nq};
+    const uint64_t strides[1] = {q_cols * 2};
     const uint32_t box[2] = {64, BM};
     if (int rc = encode_tensor_map(&tq, tdt, 2, queries, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
@@ -657,16 +716,18 @@ extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, co
     uint8_t* w = static_cast<uint8_t*>(workspace) + align256((size_t)nq * sizeof(uint32_t));
     P.tau_glob = tau_glob;
     P.lists = reinterpret_cast<uint2*>(w);
-    w += align256((size_t)pp.grid * BM * kCap * sizeof(uint2));
+    w += align256((size_t)pp.grid * BM * 32 * (size_t)epl_for_k(k) * sizeof(uint2));
     P.cand_scores = reinterpret_cast<float*>(w);
     w += align256((size_t)nq * pp.n_ranges * pp.kpad * sizeof(float));
     P.cand_ids = reinterpret_cast<int64_t*>(w);
     P.ids = pass_ids; P.id_base = pass_id_base; P.nq = nq; P.n_pass = n_rows; P.dim = dim; P.k = k; P.kpad = pp.kpad;
     P.n_qblocks = pp.n_qblocks; P.n_ranges = pp.n_ranges; P.tiles_per_range = pp.tiles_per_range; P.n_tiles = pp.n_tiles;
-    P.fmt = dtype == MMB200_F16 ? kFmtF16 : kFmtBF16;
+    P.fmt = dtype == MMB200_BF16 ? kFmtBF16 : kFmtF16;
+    P.kblocks = (int32_t)(q_cols / 64);
+    P.kb_wrap = split ? dim / 64 : P.kblocks;
     CUtensorMap tp;
     {
-      const uint64_t dims[2] = {(uint64_t)dim, (uint64_t)n_rows};
+      const uint64_t dims[2] = {p_cols, (uint64_t)n_rows};
       const uint64_t strides[1] = {row_pitch};
       const uint32_t box[2] = {64, (uint32_t)(BN / pp.cl)};   // each CTA of a cluster fetches (and multicasts) its slice
       if (int rc = encode_tensor_map(&tp, tdt, 2, passages, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -693,13 +754,13 @@ extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, co
     };
     if (out_params) *out_params = P;
 #ifdef MMB200_ENABLE_PROF
-    if (pp.cl == 1 && out_params && getenv("MMB200_FLATIP_PROF")) {  // debugging aid: per-role wait cycles
+    if (pp.cl == 1 && out_params && epl_for_k(k) == 32 && getenv("MMB200_FLATIP_PROF")) {  // debugging aid: per-role wait cycles
       long long* prof = nullptr;
       long long h[12] = {0};
       MMB_CHECK_CUDA(cudaMalloc(&prof, sizeof(h)));
       MMB_CHECK_CUDA(cudaMemset(prof, 0, sizeof(h)));
-      MMB_CHECK_CUDA(cudaFuncSetAttribute(flat_ip_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      flat_ip_tc_kernel<1, true><<<pp.grid, kThreads, smem, stream>>>(tq, tp, P, prof);
+      MMB_CHECK_CUDA(cudaFuncSetAttribute(flat_ip_tc_kernel<1, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      flat_ip_tc_kernel<1, true, 32><<<pp.grid, kThreads, smem, stream>>>(tq, tp, P, prof);
       MMB_CHECK_CUDA(cudaStreamSynchronize(stream));
       MMB_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost));
       MMB_CHECK_CUDA(cudaFree(prof));
@@ -710,13 +771,17 @@ extern "C" int mmb200_flat_ip_topk(const void* queries, const void* passages, co
       return MMB200_OK;
     }
 #endif
-    return pp.cl == 1   ? launch(flat_ip_tc_kernel<1, false>)
-           : pp.cl == 2 ? launch(flat_ip_tc_kernel<2, false>)
-                        : launch(flat_ip_tc_kernel<4, false>);
+    if (epl_for_k(k) == 32)
+      return pp.cl == 1   ? launch(flat_ip_tc_kernel<1, false, 32>)
+             : pp.cl == 2 ? launch(flat_ip_tc_kernel<2, false, 32>)
+                          : launch(flat_ip_tc_kernel<4, false, 32>);
+    return pp.cl == 1   ? launch(flat_ip_tc_kernel<1, false, 64>)
+           : pp.cl == 2 ? launch(flat_ip_tc_kernel<2, false, 64>)
+                        : launch(flat_ip_tc_kernel<4, false, 64>);
   };
 
   FipParams P{};
-  if (int rc = run_pass(pl, n_pass, (uint64_t)dim * 2, ids, id_base, &P)) return rc;
+  if (int rc = run_pass(pl, n_pass, p_cols * 2, ids, id_base, &P)) return rc;
   return launch_merge(P.cand_scores, P.cand_ids, nq, pl.n_ranges * pl.kpad, k, out_scores, out_ids, dev, stream);
 }
 

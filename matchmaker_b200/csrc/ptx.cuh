@@ -52,14 +52,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 
+// try_wait with a suspend-time hint: a warp whose phase has not completed is parked by the hardware (up to the hint)
+// instead of returning at once, so a role that waits for a slower one does not burn the SM's issue slots on a
+// try_wait / branch loop (ncu on tkl_ts_kernel: the convert warps, waiting on the epilogue-bound pipeline, executed
+// 30 % of all warp instructions before this hint was added).
+constexpr uint32_t kMbarSuspendHintNs = 0x989680u;  // 10 ms: upper bound only, the wait ends when the phase completes
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendHintNs)
       : "memory");
   return ok != 0;
 }

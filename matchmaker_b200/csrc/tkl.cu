@@ -280,17 +280,19 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P, long 
 }
 
 // One warp per document: sentinel, 3 greedy hills, neighbours, weighted sum (sigir20_tkl.py:254-286).
-__global__ void __launch_bounds__(128) tkl_hills_kernel(float* __restrict__ window_score, const float* __restrict__ chunk_scoring,
+__global__ void __launch_bounds__(128) tkl_hills_kernel(const float* window_score, float* orig_score,
+                                                        const float* __restrict__ chunk_scoring,
                                                         int64_t* __restrict__ top_idx, float* __restrict__ top15,
                                                         float* __restrict__ score, int64_t B, int W) {
   extern __shared__ float work[];  // [4 warps][W]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * 4 + warp;
   if (b >= B) return;
-  float* ws = window_score + b * W;
+  const float* win = window_score + b * W;   // may alias orig_score (in-place use)
+  float* ws = orig_score + b * W;
   float* wk = work + (size_t)warp * W;
   for (int w = lane; w < W; w += 32) {
-    float v = ws[w];
+    float v = win[w];
     if (v == 0.f) v = -9900.f;  // :257
     ws[w] = v;
     wk[w] = v;
@@ -336,9 +338,40 @@ __global__ void __launch_bounds__(128) tkl_hills_kernel(float* __restrict__ wind
     if (ws[w] <= -9900.f) ws[w] = 0.f;  // :284 (the reference's returned "orig_score")
 }
 
+// slot_to_packed[s] = (number of packed slots before s) if packed[s] else -1.  One block; n = B * C is small.
+__global__ void __launch_bounds__(1024) tkl_slot_map_kernel(const uint8_t* __restrict__ packed, int64_t n,
+                                                            int32_t* __restrict__ slot_to_packed) {
+  __shared__ int sums[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t lo = min(n, (int64_t)t * per), hi = min(n, lo + per);
+  int local = 0;
+  for (int64_t i = lo; i < hi; ++i) local += packed[i] ? 1 : 0;
+  sums[t] = local;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = t >= o ? sums[t - o] : 0;
+    __syncthreads();
+    sums[t] += v;
+    __syncthreads();
+  }
+  int run = sums[t] - local;
+  for (int64_t i = lo; i < hi; ++i) slot_to_packed[i] = packed[i] ? run++ : -1;
+}
+
 }  // namespace
 
 }  // namespace mmb
+
+extern "C" int mmb200_tkl_slot_map(const void* packed_mask, int32_t* slot_to_packed, int64_t n_slots, void* stream_) {
+  using namespace mmb;
+  MMB_REQUIRE(packed_mask && slot_to_packed && n_slots >= 0, "bad arguments");
+  if (n_slots == 0) return MMB200_OK;
+  tkl_slot_map_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<const uint8_t*>(packed_mask), n_slots,
+                                                                         slot_to_packed);
+  MMB_CHECK_CUDA(cudaGetLastError());
+  return MMB200_OK;
+}
 
 extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, const float* chunks, const void* chunk_mask,
                                         const int32_t* slot_to_packed, const float* mu, const float* sigma,
@@ -430,10 +463,10 @@ extern "C" int mmb200_tkl_window_scores(const float* q, const void* q_mask, cons
   return MMB200_OK;
 }
 
-extern "C" int mmb200_tkl_top_hills(float* window_score, const float* chunk_scoring, int64_t* top_idx, float* top15,
-                                    float* score, int64_t B, int32_t W, void* stream_) {
+extern "C" int mmb200_tkl_top_hills(const float* window_score, float* orig_score, const float* chunk_scoring,
+                                    int64_t* top_idx, float* top15, float* score, int64_t B, int32_t W, void* stream_) {
   using namespace mmb;
-  MMB_REQUIRE(window_score && chunk_scoring && top_idx && top15 && score, "null pointer");
+  MMB_REQUIRE(window_score && orig_score && chunk_scoring && top_idx && top15 && score, "null pointer");
   MMB_REQUIRE(W >= 3, "need at least 3 windows");
   if (B == 0) return MMB200_OK;
   DeviceInfo dev;
@@ -446,7 +479,7 @@ extern "C" int mmb200_tkl_top_hills(float* window_score, const float* chunk_scor
   MMB_REQUIRE(smem <= (size_t)dev.max_smem_optin, "too many windows for the hills kernel");
   MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_hills_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tkl_hills_kernel<<<(unsigned)((B + 3) / 4), 128, smem, static_cast<cudaStream_t>(stream_)>>>(
-      window_score, chunk_scoring, top_idx, top15, score, B, W);
+      window_score, orig_score, chunk_scoring, top_idx, top15, score, B, W);
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;
 }

@@ -86,10 +86,10 @@ struct TsShared {
   float red[kMaxLq];          // sat_emb_reduce1(q_i)
   float qm[kMaxLq];
   float sp[16];
-  int lenw[64];               // token count of the window ending at each pair of the tile
+  int lenw[64];               // 16 x token count of the window ending at each pair of the tile (byte offset into a sat row)
   float dmring[256];          // unmasked flag of the document's positions, indexed by position & 255
   float part[kEpiWarps][64];  // per-warp partial window scores
-  float sat1[kMaxLq * kSatStride], sat2[kMaxLq * kSatStride], sat3[kMaxLq * kSatStride];
+  float4 sat[kMaxLq * kSatStride];   // (sat1 * gate, sat2, sat3 * gate, -) per (query row, token count)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -430,8 +430,8 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const bool ik_live = et < n_ik;
       const int qi = ik_live ? et / P.K : 0;     // query row of this thread in phase B
       const int kk = ik_live ? et - qi * P.K : 0;
-      const float mu_k = P.mu[kk];
       const float a_k = sqrtf(0.5f * 1.4426950408889634f) / P.sigma[kk];
+      const float nma_k = -P.mu[kk] * a_k;        // x = (c - mu) a = c a + nma
       const float w_k = ik_live ? P.dense_w[kk] : 0.f;
       const float km_k = SAT == 1 ? P.sat_params[kk] : 1.f;
       float suf[kBlk];
@@ -479,9 +479,9 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
               const float rstd = rsqrtf((d0 * d0 + d1 * d1) * 0.5f + 1e-5f);
               const float y0 = d0 * rstd * sp[0] + sp[2], y1 = d1 * rstd * sp[1] + sp[3];
               const float gate = (S->qm[i] != 0.f && len > 0) ? 1.f : 0.f;
-              S->sat1[i * kSatStride + len] = (y0 * sp[4] + y1 * sp[5] + sp[6]) * gate;
-              S->sat2[i * kSatStride + len] = 1.0f / (y0 * sp[7] + y1 * sp[8] + sp[9]);
-              S->sat3[i * kSatStride + len] = (y0 * sp[10] + y1 * sp[11] + sp[12]) * gate;
+              S->sat[i * kSatStride + len] = make_float4((y0 * sp[4] + y1 * sp[5] + sp[6]) * gate,
+                                                         1.0f / (y0 * sp[7] + y1 * sp[8] + sp[9]),
+                                                         (y0 * sp[10] + y1 * sp[11] + sp[12]) * gate, 0.f);
             }
           }
           qm_i = S->qm[qi];   // written before the barrier above
@@ -535,41 +535,49 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             const int pos = last - u;
             if (pos >= 0) n += S->dmring[pos & 255];
           }
-          S->lenw[et] = (int)n;
+          S->lenw[et] = 16 * (int)n;
         }
         named_bar_sync(3, kEpiThreads);
         // ---- phase B: activations, block prefix / suffix, windows ------------------------------------------------
         if (ew < n_act_warps) {
-          const int wbase = t * kTilePairs - (kBlk - 1);      // window index of the tile's pair 0
-          for (int j = tw.halo ? kBlocks - 1 : 0; j < kBlocks; ++j) {
-            float tv[16];
-            float pre = 0.f;
-            const float* cblk = cs + (2 * kBlk * j) * kCsStride + qi;
+          if (tw.halo) {
+            // halo tile: only the suffix sums of its last block are wanted
+            const float* cblk = cs + (2 * kBlk * (kBlocks - 1)) * kCsStride + qi;
 #pragma unroll
             for (int r = 0; r < kBlk; ++r) {
-              const float c0 = cblk[(2 * r) * kCsStride], c1 = cblk[(2 * r + 1) * kCsStride];
-              const float x0 = (c0 - mu_k) * a_k, x1 = (c1 - mu_k) * a_k;
-              const float u = ex2f(-x0 * x0) + ex2f(-x1 * x1);
-              pre = r == 0 ? u : pre + u;
-              const float Ssum = r < kBlk - 1 ? suf[r + 1] + pre : pre;
-              suf[r] = u;   // suf[r] of the previous block was consumed by window r - 1
-              const int w = wbase + kBlk * j + r;
-              float tvv = 0.f;
-              if (!tw.halo && w >= 0 && w < P.W) {   // warp-uniform
-                const int len = S->lenw[kBlk * j + r];
-                if (SAT == 0) {
-                  const int ti = qi * kSatStride + len;
-                  const float pw = ex2f(S->sat2[ti] * lg2f(fmaxf(Ssum, kClamp)));
-                  tvv = w_k * (S->sat1[ti] * pw - S->sat3[ti]);
-                } else {
-                  tvv = (len > 0 && qm_i != 0.f) ? w_k * logf(fmaxf(Ssum * km_k, kClamp)) : 0.f;
-                }
-              }
-              tv[r] = tvv;
+              const float x0 = fmaf(cblk[(2 * r) * kCsStride], a_k, nma_k), x1 = fmaf(cblk[(2 * r + 1) * kCsStride], a_k, nma_k);
+              suf[r] = ex2f(-x0 * x0) + ex2f(-x1 * x1);
             }
 #pragma unroll
             for (int r = kBlk - 2; r >= 0; --r) suf[r] += suf[r + 1];
-            if (!tw.halo) {
+          } else {
+            // Windows that fall outside [0, W) (first block of a document, tail of the last tile) are computed like
+            // the others -- from stale suffix sums or padding -- and dropped by the range check of the final write.
+            const uint8_t* sat_row = reinterpret_cast<const uint8_t*>(S->sat + qi * kSatStride);
+            for (int j = 0; j < kBlocks; ++j) {
+              float tv[16];
+              float pre = 0.f;
+              const float* cblk = cs + (2 * kBlk * j) * kCsStride + qi;
+              const int* lw = S->lenw + kBlk * j;
+#pragma unroll
+              for (int r = 0; r < kBlk; ++r) {
+                const float x0 = fmaf(cblk[(2 * r) * kCsStride], a_k, nma_k), x1 = fmaf(cblk[(2 * r + 1) * kCsStride], a_k, nma_k);
+                const float u = ex2f(-x0 * x0) + ex2f(-x1 * x1);
+                pre = r == 0 ? u : pre + u;
+                const float Ssum = r < kBlk - 1 ? suf[r + 1] + pre : pre;
+                suf[r] = u;   // suf[r] of the previous block was consumed by window r - 1
+                const int lenb = lw[r];
+                if (SAT == 0) {
+                  const float4 st = *reinterpret_cast<const float4*>(sat_row + lenb);
+                  const float pw = ex2f(st.y * lg2f(fmaxf(Ssum, kClamp)));
+                  tv[r] = w_k * fmaf(st.x, pw, -st.z);
+                } else {
+                  const float lg = 0.6931471805599453f * lg2f(fmaxf(Ssum * km_k, kClamp));
+                  tv[r] = (lenb > 0 && qm_i != 0.f) ? w_k * lg : 0.f;
+                }
+              }
+#pragma unroll
+              for (int r = kBlk - 2; r >= 0; --r) suf[r] += suf[r + 1];
               tv[15] = 0.f;
               // transposed butterfly: 16 values x 32 lanes -> lane l holds the warp total of value l >> 1
 #pragma unroll

@@ -33,6 +33,7 @@ class FlatIPIndexer(BaseNNIndexer):
         self.passages: Optional[torch.Tensor] = None   # [n_local, dim] fp16 on self.device
         self.ids: Optional[torch.Tensor] = None        # [n_local] int64
         self.n_total = 0
+        self.split_scale = None
 
     def _world(self):
         import torch.distributed as dist
@@ -53,7 +54,7 @@ class FlatIPIndexer(BaseNNIndexer):
         if hi > lo:
             with torch.cuda.device(self.device):
                 vecs = blocks_to_device(data_chunks, lo, hi, self.device)
-            self.passages = vecs if vecs.dtype == self.store_dtype else vecs.to(self.store_dtype)
+            self._set_passages(vecs)
             id_parts, off = [], 0
             for i_arr in ids:
                 a, b = max(lo, off), min(hi, off + len(i_arr))
@@ -62,26 +63,35 @@ class FlatIPIndexer(BaseNNIndexer):
                 off += len(i_arr)
             self.ids = torch.cat(id_parts).to(self.device)
         else:
-            self.passages = torch.empty((0, self.token_dim), dtype=self.store_dtype, device=self.device)
+            self._set_passages(torch.empty((0, self.token_dim), dtype=self.store_dtype, device=self.device))
             self.ids = torch.empty(0, dtype=torch.int64, device=self.device)
+
+    def _set_passages(self, vecs: torch.Tensor):
+        """fp16 storage as is; fp32 storage (token_dtype float32, faiss without useFloat16) as the fp16 hi / lo split the
+        kernel consumes -- same bytes per passage as fp32, 22 mantissa bits per value."""
+        if self.store_dtype == torch.float16:
+            self.passages, self.split_scale = vecs.to(torch.float16), None
+        else:
+            self.passages, self.split_scale = interaction.flat_ip_split_f32(vecs.float(), "passages")
 
     def search(self, query_vec: numpy.ndarray, top_n: int):
         if self.passages is None:
             raise _lib.MatchmakerB200Error("search() before index()")
         if query_vec.ndim == 1:
             query_vec = query_vec[numpy.newaxis, :]
-        q = torch.from_numpy(numpy.ascontiguousarray(query_vec)).to(self.device, dtype=torch.float16)
+        q = torch.from_numpy(numpy.ascontiguousarray(query_vec)).to(
+            self.device, dtype=torch.float16 if self.store_dtype == torch.float16 else torch.float32)
         scores, ids = self.search_device(q, top_n)
         return scores.cpu().numpy(), ids.cpu().numpy()
 
     def search_device(self, q: torch.Tensor, top_n: int):
         """Same as search() but device tensors in/out (no host round trip)."""
         rank, world = self._world()
-        k_local = min(top_n, 256)
-        if top_n > 256:
-            raise _lib.MatchmakerB200Error("top_n > 256 is not supported by the fused top-k kernel yet")
+        if top_n > interaction.FLAT_IP_MAX_K:
+            raise _lib.MatchmakerB200Error(f"top_n > {interaction.FLAT_IP_MAX_K} is not supported by the fused top-k kernel")
+        k_local = top_n
         if self.passages.shape[0] > 0:
-            s, i = interaction.flat_ip_topk(q, self.passages, k_local, ids=self.ids)
+            s, i = interaction.flat_ip_topk(q, self.passages, k_local, ids=self.ids, split_scale=self.split_scale)
         else:
             s = torch.full((q.shape[0], k_local), -3.4028234663852886e38, device=self.device)
             i = torch.full((q.shape[0], k_local), -1, dtype=torch.int64, device=self.device)
@@ -98,7 +108,7 @@ class FlatIPIndexer(BaseNNIndexer):
         (`<path>.rank<r>of<w>` when the job has more than one rank -- every rank owns a different slab, so they must
         not write the same file), each recording its row range and the world size it was cut for."""
         rank, world = self._world()
-        torch.save({"passages": self.passages.cpu(), "ids": self.ids.cpu(), "n_total": self.n_total,
+        torch.save({"passages": self.passages.cpu(), "split_scale": self.split_scale, "ids": self.ids.cpu(), "n_total": self.n_total,
                     "lo": getattr(self, "lo", 0), "hi": getattr(self, "hi", self.n_total), "world": world, "rank": rank,
                     "token_dtype": str(self.store_dtype)}, self._shard_path(path))
 
@@ -112,6 +122,9 @@ class FlatIPIndexer(BaseNNIndexer):
                 f"index file {self._shard_path(path)} holds rows [{blob.get('lo')},{blob.get('hi')}) of rank {saved_rank} of "
                 f"{saved_world}; this job is rank {rank} of {world} and needs rows [{lo},{hi}) -- re-index or load with the "
                 "same world size")
-        self.passages = blob["passages"].to(self.device, dtype=self.store_dtype)
+        if blob.get("token_dtype", "torch.float16") != str(self.store_dtype):
+            raise _lib.MatchmakerB200Error(f"index file was written with token_dtype {blob.get('token_dtype')}, this indexer "
+                                           f"is configured for {self.store_dtype}")
+        self.passages, self.split_scale = blob["passages"].to(self.device), blob.get("split_scale")
         self.ids = blob["ids"].to(self.device)
         self.n_total, self.lo, self.hi = blob["n_total"], lo, hi

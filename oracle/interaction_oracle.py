@@ -116,6 +116,68 @@ def kernel_pool_tk(q: torch.Tensor, d: torch.Tensor, q_mask: torch.Tensor, d_mas
                    "per_kernel_query": per_kernel_query}
 
 
+def kernel_pool_tk_sparse(q: torch.Tensor, d: torch.Tensor, q_mask: torch.Tensor, d_mask: torch.Tensor,
+                          doc_stop_words: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor, alpha: torch.Tensor,
+                          weight: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """CIKM20_TK_Sparse.forward interaction part, models/published/cikm20_tk_sparse.py:106-145.
+
+    q, d contextualised embeddings; ``doc_stop_words`` [B, Ld] is the learned per-document-term gate the reference
+    computes at :132-133 (``relu(stop_word_reducer2(tanh(stop_word_reducer(.)))) * document_mask``) -- an input here,
+    it multiplies every kernel activation of its document term (:135)."""
+    mu = mu.view(1, 1, 1, -1)
+    sigma = sigma.view(1, 1, 1, -1)
+    qd_mask = torch.bmm(q_mask.unsqueeze(-1), d_mask.unsqueeze(-1).transpose(-1, -2))      # :106
+    cos = cosine_matrix(q, d)                                                             # :114
+    cos_masked = cos * qd_mask                                                            # :115
+    raw = torch.exp(-torch.pow(cos_masked.unsqueeze(-1) - mu, 2) / (2 * torch.pow(sigma, 2)))  # :123
+    masked = raw * qd_mask.unsqueeze(-1) * doc_stop_words.unsqueeze(1).unsqueeze(-1)       # :135
+    per_kernel_query = torch.sum(masked, 2)                                               # :141
+    log_pkq = torch.log(torch.clamp(per_kernel_query * alpha.view(1, 1, -1), min=1e-10))  # :142
+    log_pkq = log_pkq * q_mask.unsqueeze(-1)                                              # :143
+    per_kernel = torch.sum(log_pkq, 1)                                                    # :144
+    score = per_kernel @ weight.view(-1)                                                  # :145
+    return score, {"score": score, "per_kernel": per_kernel, "cosine_matrix_masked": cos_masked,
+                   "per_kernel_query": per_kernel_query}
+
+
+def conv_knrm_cross_match(q_grams: List[torch.Tensor], d_grams: List[torch.Tensor], q_mask: torch.Tensor,
+                          d_mask: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor, dense_weight: torch.Tensor
+                          ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Conv_KNRM.forward after the n-gram convolutions, models/conv_knrm.py:121-170: every query n-gram tensor is
+    kernel-pooled against every document n-gram tensor (:125-127 -> forward_matrix_kernel_pooling :144-170, KNRM-style
+    masking and the 0.01 log scale), the n*n per-kernel vectors are concatenated (:133) and go through
+    ``dense`` = Linear(K*n*n, 1, bias=False) (:135).  Returns (score [B], all_grams [B, n*n*K])."""
+    mu4 = mu.view(1, 1, 1, -1)
+    sg4 = sigma.view(1, 1, 1, -1)
+    qd_mask = torch.bmm(q_mask.unsqueeze(-1), d_mask.unsqueeze(-1).transpose(-1, -2))      # :100
+    out = []
+    for qg in q_grams:                                                                    # :125
+        for dg in d_grams:                                                                # :126
+            cos = cosine_matrix(qg, dg) * qd_mask                                         # :151-152
+            raw = torch.exp(-torch.pow(cos.unsqueeze(-1) - mu4, 2) / (2 * torch.pow(sg4, 2)))  # :161
+            masked = raw * qd_mask.unsqueeze(-1)                                          # :162
+            pkq = torch.sum(masked, 2)                                                    # :164
+            lpkq = torch.log(torch.clamp(pkq, min=1e-10)) * 0.01                          # :165
+            lpkq = lpkq * q_mask.unsqueeze(-1)                                            # :166
+            out.append(torch.sum(lpkq, 1))                                                # :168
+    all_grams = torch.cat(out, 1)                                                         # :133
+    return all_grams @ dense_weight.view(-1), all_grams                                   # :135-138
+
+
+def idcm_esm_patch_scores(q_ctx: torch.Tensor, d_ctx: torch.Tensor, q_mask: torch.Tensor, d_mask: torch.Tensor,
+                          mu: torch.Tensor, sigma: torch.Tensor, alpha: torch.Tensor, weight: torch.Tensor,
+                          bias: torch.Tensor) -> torch.Tensor:
+    """IDCM's ESM patch scorer, models/published/sigir21_idcm.py:182-186: q_ctx / d_ctx are ALREADY L2-normalised
+    (F.normalize, :164-178) so the match matrix is a plain bmm (:182); kernels masked by the patch mask only (:184);
+    clamp floor 1e-4 (not 1e-10) on alpha*S (:185); ``sampling_binweights`` = Linear(11, 1, bias=True) (:100, :186).
+    PARITY UNPINNED: the class needs HF BERT weights to construct, the lines are restated."""
+    cos = torch.bmm(q_ctx, d_ctx.transpose(-1, -2)).unsqueeze(-1)                         # :182
+    act = torch.exp(-torch.pow(cos - mu.view(1, 1, 1, -1), 2) / (2 * torch.pow(sigma.view(1, 1, 1, -1), 2))) \
+        * d_mask.unsqueeze(-1).unsqueeze(1)                                               # :184
+    res = torch.log(torch.clamp(torch.sum(act, 2) * alpha.view(1, 1, -1), min=1e-4)) * q_mask.unsqueeze(-1)  # :185
+    return torch.sum(res, 1) @ weight.view(-1) + bias.view(-1)[0]                         # :186
+
+
 # ----------------------------------------------------------------------------
 # ColBERT max-sim
 # ----------------------------------------------------------------------------

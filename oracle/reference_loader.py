@@ -137,6 +137,19 @@ def load_tkl(emb: int, mu, sigma, heads: int = 10, layers: int = 2, ff: int = 30
         return mod.TKL_sigir20(emb, list(mu), list(sigma), heads, layers, ff, max_len, use_pos, diff_pos, saturation)
 
 
+def load_tk_sparse(emb: int, mu, sigma, heads: int = 4, layers: int = 1, proj: int = 16, ff: int = 32, max_len: int = 64,
+                   diff_pos: bool = True):
+    mod = _load("matchmaker/models/published/cikm20_tk_sparse.py", "_ref_tk_sparse")
+    with _shimmed():
+        return mod.CIKM20_TK_Sparse(emb, list(mu), list(sigma), heads, layers, proj, ff, max_len, diff_pos)
+
+
+def load_conv_knrm(emb: int, n_grams: int = 3, n_kernels: int = 11, conv_out: int = 32):
+    mod = _load("matchmaker/models/conv_knrm.py", "_ref_conv_knrm")
+    with _shimmed():
+        return mod.Conv_KNRM(emb, n_grams, n_kernels, conv_out)
+
+
 class _Passthrough:
     """forward_representation replacement: tokens dict carries the vectors."""
 

@@ -60,7 +60,7 @@ def test_flat_ip_plan_invariants(sm_count):
     out = (ctypes.c_int32 * 8)()
     for nq in (1, 127, 128, 129, 1300, 6400, 100000):
         for n_pass in (1, 255, 256, 257, 70000, 1100000, 8800000):
-            for k in (1, 100, 256):
+            for k in (1, 100, 256, 257, 1000, 1024):
                 assert lib.mmb200_flat_ip_plan(nq, n_pass, k, sm_count, out) == _lib.OK, _lib.last_error()
                 n_qb, n_tiles, n_ranges, tpr, grid, cl, ws_lo, ws_hi = [int(v) for v in out]
                 ws = (ws_lo & 0xffffffff) | ((ws_hi & 0xffffffff) << 32)
@@ -69,8 +69,9 @@ def test_flat_ip_plan_invariants(sm_count):
                 assert cl in (1, 2, 4) and grid >= cl and grid % cl == 0 and grid <= max(cl, sm_count)
                 n_groups = (n_qb + cl - 1) // cl
                 assert grid <= cl * n_groups * n_ranges          # no CTA without a work item
-                assert ws >= nq * 4 + grid * 128 * 1024 * 8      # thresholds + one 1024-entry list per row per CTA
+                cap = 1024 if k <= 256 else 2048
+                assert ws >= nq * 4 + grid * 128 * cap * 8       # thresholds + one candidate list per row per CTA
                 kpad = (k + 31) // 32 * 32
                 assert ws >= nq * n_ranges * kpad * 12           # (score, id) candidates per query and range
     assert lib.mmb200_flat_ip_plan(0, 10, 1, sm_count, out) == _lib.ERR_INVALID
-    assert lib.mmb200_flat_ip_plan(10, 10, 257, sm_count, out) == _lib.ERR_INVALID
+    assert lib.mmb200_flat_ip_plan(10, 10, 1025, sm_count, out) == _lib.ERR_INVALID

@@ -52,13 +52,77 @@ def test_topk_merge_kernel():
     g = torch.Generator().manual_seed(5)
     s = torch.randn(9, 700, generator=g)
     s[:, 100:110] = s[:, 5:6]  # ties
-    ids = torch.stack([torch.randperm(100000, generator=g)[:700] for _ in range(9)])
-    ids[:, 650:] = -1
+    ids = torch.stack([torch.randperm(100000, generator=g)[:700] for _ in range(9)]) - 50000   # negative user ids are ids
+    s[:, 650:] = float("-inf")          # void candidates are marked by their SCORE (-inf / -FLT_MAX / NaN), not by the id
+    s[:, 640:650] = -3.4028234663852886e38
     ms, mi = interaction.topk_merge(s.to(DEV), ids.to(DEV), 64)
     for r in range(9):
-        valid = ids[r] >= 0
+        valid = s[r] > -3.0e38
         rs, ri = O.rank_desc_stable(s[r][valid], ids[r][valid], 64)
         assert torch.equal(mi[r].cpu(), ri) and torch.equal(ms[r].cpu(), rs)
+
+
+def test_topk_merge_many_candidates_in_passes():
+    """More candidates per query than one shared-memory sort holds (8192): merged in passes, same total order."""
+    g = torch.Generator().manual_seed(6)
+    nq, L, k = 5, 30000, 300
+    s = torch.randn(nq, L, generator=g)
+    s[:, 7000:7050] = s[:, 3:4]          # ties across pass boundaries
+    ids = torch.stack([torch.randperm(10 ** 6, generator=g)[:L] for _ in range(nq)]) - 500000
+    ms, mi = interaction.topk_merge(s.to(DEV), ids.to(DEV), k)
+    for r in range(nq):
+        rs, ri = O.rank_desc_stable(s[r], ids[r], k)
+        assert torch.equal(mi[r].cpu(), ri) and torch.equal(ms[r].cpu(), rs)
+
+
+@pytest.mark.parametrize("shape", [(40, 30000, 128, 1000), (130, 9000, 64, 300), (3, 500, 64, 1024), (300, 50000, 64, 1000)])
+def test_large_k(shape):
+    """top_n beyond 256 (dense_retrieval.py:391 passes any top_n; index_hit_top_n raises it to 1000): 2048-entry lists."""
+    nq, n, dim, k = shape
+    q, p = O.synth_dense_inputs(nq, n, dim, seed=nq + n + k)
+    ids = torch.randperm(n, generator=torch.Generator().manual_seed(2)) * 5 - 1000   # some negative ids
+    s, i = interaction.flat_ip_topk(q.to(DEV), p.to(DEV), k, ids=ids.to(DEV))
+    _check(q, p, ids, k, s, i)
+
+
+@pytest.mark.parametrize("shape", [(9, 4000, 64, 10), (70, 30000, 128, 100), (16, 6000, 768, 100)])
+def test_fp32_storage_split(shape):
+    """token_dtype float32 (faiss_indices.py:65,72: no useFloat16): fp32 vectors held as fp16 hi/lo halves; the result
+    must track the fp64 ranking of the FP32 inputs (ids exact outside fp64 near-ties) and the scores to 1e-5 relative."""
+    nq, n, dim, k = shape
+    q, p = O.synth_dense_inputs(nq, n, dim, seed=nq + n, dtype=torch.float32)
+    p[5] *= 37.0                                  # wide dynamic range inside one shard
+    p[6] *= 1e-3
+    ids = torch.arange(n) * 2 + 1
+    ps, scale = interaction.flat_ip_split_f32(p.to(DEV), "passages")
+    assert ps.shape == (n, 2 * dim) and ps.dtype == torch.float16
+    s, i = interaction.flat_ip_topk(q.to(DEV), ps, k, ids=ids.to(DEV), split_scale=scale)
+    s64 = q.double() @ p.double().T
+    ref_s, ref_pos = torch.topk(s64, k, dim=1)
+    got_s = s.cpu().double()
+    assert ((got_s - ref_s).abs() <= 1e-5 * ref_s.abs().clamp(min=1.0)).all(), (got_s - ref_s).abs().max()
+    ref_i = ids[ref_pos]
+    gaps = (ref_s[:, :-1] - ref_s[:, 1:])
+    decided = torch.ones_like(ref_i, dtype=torch.bool)
+    tol = 2e-5 * ref_s.abs().clamp(min=1.0)
+    decided[:, 1:] &= gaps > tol[:, 1:]
+    decided[:, :-1] &= gaps > tol[:, :-1]
+    assert (i.cpu()[decided] == ref_i[decided]).all()
+    assert decided.float().mean() > 0.95
+
+
+def test_indexer_fp32_and_large_top_n():
+    from matchmaker_b200.retrieval import FlatIPIndexer
+    idx = FlatIPIndexer({"token_dim": 64, "faiss_use_gpu": True, "token_dtype": "float32"})
+    q, p = O.synth_dense_inputs(7, 3000, 64, seed=12, dtype=torch.float32)
+    ids = np.arange(3000, dtype=np.int64) - 1500
+    idx.index([ids], [p.numpy()])
+    s, i = idx.search(q.numpy(), 400)
+    assert s.shape == (7, 400) and i.shape == (7, 400)
+    s64 = q.double() @ p.double().T
+    ref_s, ref_pos = torch.topk(s64, 400, dim=1)
+    assert np.allclose(s, ref_s.numpy(), rtol=1e-5, atol=1e-5)
+    assert (i == ids[ref_pos.numpy()]).mean() > 0.98
 
 
 def test_baseline_cfg4_slab_properties():
