@@ -161,6 +161,31 @@ MMB200_API int mmb200_kernel_pool_bwd(const float* q, const float* d, const void
                                       int32_t Lq, int32_t Ld, int32_t D, int32_t K, float log_scale,
                                       int32_t mask_dtype, void* stream);
 
+/* Variants of the same pooling -- mmb200_kernel_pool_fwd / _bwd are these with doc_gate = NULL,
+ * clamp_min = 1e-10, score_bias = 0:
+ *   doc_gate [B, Ld] f32 or NULL: multiplier of every activation of document term j (negative values count as 0),
+ *            S_ik = sum_j d_mask[j] * doc_gate[j] * exp(...).  Replaces the `* document_stop_words` of
+ *            CIKM20_TK_Sparse.forward, matchmaker/models/published/cikm20_tk_sparse.py:135.
+ *   clamp_min: floor of alpha_k * S_ik before the log.  IDCM's ESM patch scorer uses 1e-4
+ *            (matchmaker/models/published/sigir21_idcm.py:185).
+ *   score_bias: added to the score (the bias of IDCM's `sampling_binweights` Linear(11, 1), sigir21_idcm.py:100,186).
+ *   Conv-KNRM's n x n cross matches (matchmaker/models/conv_knrm.py:125-135) are n*n calls with log_scale = 0.01, each
+ *   taking its K-slice of dense.weight (Linear over a concatenation = sum of per-block Linears).
+ * Backward additionally returns grad_gate [B, Ld] (or NULL): d(loss)/d(doc_gate). */
+MMB200_API int mmb200_kernel_pool_fwd_ex(const float* q, const float* d, const void* q_mask, const void* d_mask,
+                                         const float* doc_gate, const float* mu, const float* sigma, const float* alpha,
+                                         const float* weight, float* score, float* per_kernel, float* per_kernel_query,
+                                         float* cosine, int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K,
+                                         float log_scale, float clamp_min, float score_bias, int32_t mask_dtype,
+                                         int32_t impl, void* stream);
+MMB200_API int mmb200_kernel_pool_bwd_ex(const float* q, const float* d, const void* q_mask, const void* d_mask,
+                                         const float* doc_gate, const float* mu, const float* sigma, const float* alpha,
+                                         const float* weight, const float* per_kernel_query, const float* grad_score,
+                                         float* grad_q, float* grad_d, float* grad_gate, float* grad_alpha,
+                                         float* grad_weight, float* workspace, int64_t B, int32_t Lq, int32_t Ld,
+                                         int32_t D, int32_t K, float log_scale, float clamp_min, int32_t mask_dtype,
+                                         void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * BERT_DOT pair scoring: out[b] = <q[b], d[b]>, fp32 accumulate.
  * Replaces: BERT_Dot.forward   matchmaker/models/bert_dot.py:62  (bmm([B,1,dim],[B,dim,1]))

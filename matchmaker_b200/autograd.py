@@ -37,36 +37,41 @@ def maxsim(q: torch.Tensor, d: torch.Tensor, q_mask: Optional[torch.Tensor] = No
 
 class _KernelPool(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale):
+    def forward(ctx, q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale, doc_gate, clamp_min, bias):
         # needs_input_grad (not tensor.requires_grad: parameters always require grad, also under no_grad)
-        need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 6, 7))
+        need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 6, 7, 9))
         out = interaction.kernel_pool(q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale,
-                                      want_per_kernel=True, want_per_kernel_query=need_grad)
+                                      want_per_kernel=True, want_per_kernel_query=need_grad, doc_gate=doc_gate,
+                                      clamp_min=clamp_min, bias=bias)
         if need_grad:
-            ctx.save_for_backward(q, d, q_mask, d_mask, mu, sigma, weight,
-                                  alpha if alpha is not None else torch.empty(0, device=q.device),
-                                  out["per_kernel_query"])
-            ctx.has_alpha = alpha is not None
-            ctx.log_scale = log_scale
+            empty = torch.empty(0, device=q.device)
+            ctx.save_for_backward(q, d, q_mask, d_mask, mu, sigma, weight, alpha if alpha is not None else empty,
+                                  out["per_kernel_query"], doc_gate if doc_gate is not None else empty)
+            ctx.has_alpha, ctx.has_gate = alpha is not None, doc_gate is not None
+            ctx.log_scale, ctx.clamp_min = log_scale, clamp_min
         ctx.mark_non_differentiable(out["per_kernel"])
         return out["score"], out["per_kernel"]
 
     @staticmethod
     def backward(ctx, grad_score, _grad_pk):
-        q, d, q_mask, d_mask, mu, sigma, weight, alpha, S = ctx.saved_tensors
+        q, d, q_mask, d_mask, mu, sigma, weight, alpha, S, gate = ctx.saved_tensors
         alpha = alpha if ctx.has_alpha else None
-        gq, gd, ga, gw = interaction.kernel_pool_bwd(q, d, q_mask, d_mask, mu, sigma, weight, alpha, S, grad_score,
-                                                     ctx.log_scale)
+        gate = gate if ctx.has_gate else None
+        res = interaction.kernel_pool_bwd(q, d, q_mask, d_mask, mu, sigma, weight, alpha, S, grad_score, ctx.log_scale,
+                                          doc_gate=gate, clamp_min=ctx.clamp_min)
+        gq, gd, ga, gw = res[:4]
+        gg = res[4].view_as(gate) if gate is not None else None
         gw = gw.view_as(weight)
         ga = None if ga is None else ga.view_as(alpha)
-        return gq.to(q.dtype), gd.to(d.dtype), None, None, None, None, gw, ga, None
+        return gq.to(q.dtype), gd.to(d.dtype), None, None, None, None, gw, ga, None, gg, None, None
 
 
-def kernel_pool(q, d, q_mask, d_mask, mu, sigma, weight, alpha=None, log_scale: float = 1.0):
+def kernel_pool(q, d, q_mask, d_mask, mu, sigma, weight, alpha=None, log_scale: float = 1.0, doc_gate=None,
+                clamp_min: float = 1e-10, bias: float = 0.0):
     """Differentiable cosine + RBF kernel pooling: returns (score [B], per_kernel [B,K]); gradients flow to
-    q, d, weight and alpha through the score (per_kernel is a detached by-product, as used by the
-    reference's secondary outputs)."""
-    return _KernelPool.apply(q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale)
+    q, d, weight, alpha and doc_gate through the score (per_kernel is a detached by-product, as used by the
+    reference's secondary outputs).  doc_gate / clamp_min / bias: see :func:`interaction.kernel_pool`."""
+    return _KernelPool.apply(q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale, doc_gate, clamp_min, bias)
 
 
 class _DotPairs(torch.autograd.Function):

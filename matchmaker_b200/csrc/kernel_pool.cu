@@ -25,7 +25,6 @@ namespace mmb {
 constexpr int kKpThreads = 256;
 constexpr int kKpQ = 32;            // query rows per block pass
 constexpr float kTinyNorm = 1e-13f; // allennlp tiny_value_of_dtype(float32)
-constexpr float kClampMin = 1e-10f; // knrm.py:74, ecai20_tk.py:121
 
 __host__ __device__ inline int kp_row_stride(int D) {
   int dp = (D + 3) & ~3;
@@ -159,7 +158,10 @@ __global__ void __launch_bounds__(kKpThreads) kernel_pool_fwd_simt(KpParams P) {
       for (int j0 = 0; j0 < Ld; j0 += TJ) {
         __syncthreads();  // previous tile fully consumed
         kp_load_rows(db, j0, Ld, D, dp, TJ, ds, nullptr, nullptr);
-        if (t < TJ) dm_s[t] = (j0 + t < Ld && mask_at(P.d_mask, P.d_mask ? P.mask_dtype : 0, b * (int64_t)Ld + j0 + t)) ? 1.f : 0.f;
+        if (t < TJ) {   // dm_s = mask x gate: the weight of document term j in every activation sum
+          const bool live = j0 + t < Ld && mask_at(P.d_mask, P.d_mask ? P.mask_dtype : 0, b * (int64_t)Ld + j0 + t);
+          dm_s[t] = live ? (P.gate ? fmaxf(P.gate[b * (int64_t)Ld + j0 + t], 0.f) : 1.f) : 0.f;
+        }
         __syncthreads();
         kp_cos_tile<JR>(qs, ds, D, dp, cs, TJ + 1);
         __syncthreads();
@@ -167,7 +169,9 @@ __global__ void __launch_bounds__(kKpThreads) kernel_pool_fwd_simt(KpParams P) {
           for (int e = t; e < kKpQ * TJ; e += kKpThreads) {
             const int i = e / TJ, j = e % TJ;
             if (i0 + i < Lq && j0 + j < Ld)
-              P.cosine[(b * Lq + i0 + i) * (int64_t)Ld + j0 + j] = cs[i * (TJ + 1) + j] * qm_s[i] * dm_s[j];
+              P.cosine[(b * Lq + i0 + i) * (int64_t)Ld + j0 + j] =
+                  cs[i * (TJ + 1) + j] * qm_s[i] *
+                  (mask_at(P.d_mask, P.d_mask ? P.mask_dtype : 0, b * (int64_t)Ld + j0 + j) ? 1.f : 0.f);
           }
         }
         {  // kernel activations: thread = (query row i, eighth of the tile's document rows)
@@ -175,12 +179,13 @@ __global__ void __launch_bounds__(kKpThreads) kernel_pool_fwd_simt(KpParams P) {
 #pragma unroll 1
           for (int jj = 0; jj < TJ / 8; ++jj) {
             const int j = jg * (TJ / 8) + jj;
-            if (dm_s[j] != 0.f) {  // warp-uniform
+            const float gj = dm_s[j];
+            if (gj != 0.f) {  // warp-uniform
               const float c = cs[i * (TJ + 1) + j];
 #pragma unroll
               for (int k = 0; k < KB; ++k) {
                 const float u = (c - mu_s[k]) * a_s[k];
-                acc[k] += ex2_approx(-u * u);
+                acc[k] = fmaf(gj, ex2_approx(-u * u), acc[k]);
               }
             }
           }
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(kKpThreads) kernel_pool_fwd_simt(KpParams P) {
         float L = 0.f;
         if (k < K && i0 + i < Lq) {
           if (P.per_kernel_query) P.per_kernel_query[(b * Lq + i0 + i) * (int64_t)K + k] = S;
-          if (qm_s[i] != 0.f) L = P.log_scale * logf(fmaxf(S * al_s[k], kClampMin));
+          if (qm_s[i] != 0.f) L = P.log_scale * logf(fmaxf(S * al_s[k], P.clamp_min));
         }
         lsm[k * 32 + i] = L;
       }
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(kKpThreads) kernel_pool_fwd_simt(KpParams P) {
     if (t == 0) {
       float s = 0.f;
       for (int k = 0; k < K; ++k) s = fmaf(pk_s[k], w_s[k], s);
-      P.score[b] = s;
+      P.score[b] = s + P.bias;
     }
   }
 }
@@ -277,8 +282,8 @@ __global__ void __launch_bounds__(kKpThreads) kernel_pool_bwd_simt(KpParams P) {
         if (k < K && i0 + i < Lq && qm_s[i] != 0.f) {
           const float S = P.S[(b * Lq + i0 + i) * (int64_t)K + k];
           const float aS = S * al_s[k];
-          Lv = P.log_scale * logf(fmaxf(aS, kClampMin));
-          if (aS >= kClampMin) {  // torch.clamp passes the gradient at equality
+          Lv = P.log_scale * logf(fmaxf(aS, P.clamp_min));
+          if (aS >= P.clamp_min) {  // torch.clamp passes the gradient at equality
             cf = g * w_s[k] * P.log_scale / S;
             da = g * w_s[k] * P.log_scale / al_s[k];
           }
@@ -310,22 +315,35 @@ __global__ void __launch_bounds__(kKpThreads) kernel_pool_bwd_simt(KpParams P) {
         __syncthreads();
         kp_cos_tile<1>(qs, ds, D, dp, cs, 33);
         __syncthreads();
-        {  // G_ij = dm_j sum_k dS_ik K_ijk (-(c-mu_k)/sigma_k^2)
+        {  // G_ij = dm_j g_j sum_k dS_ik K_ijk (-(c-mu_k)/sigma_k^2);  d gate_j = dm_j sum_i sum_k dS_ik K_ijk
           const int i = lane;
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int j = warp + 8 * jj;
-            float G = 0.f;
-            if (dm_s[j] != 0.f) {
+            float G = 0.f, H = 0.f;
+            if (dm_s[j] != 0.f) {   // warp-uniform
               const float c = cs[i * 33 + j];
 #pragma unroll
               for (int k = 0; k < KB; ++k) {
                 const float diff = c - mu_s[k];
                 const float u = diff * a_s[k];
-                G = fmaf(coef[i * KB + k] * ex2_approx(-u * u), -diff * is2_s[k], G);
+                const float ck = coef[i * KB + k] * ex2_approx(-u * u);
+                G = fmaf(ck, -diff * is2_s[k], G);
+                H += ck;
               }
+              if (P.gate) G *= fmaxf(P.gate[b * (int64_t)Ld + j0 + j], 0.f);
             }
             Gs[j * 32 + i] = G;
+            if (P.grad_gate && j0 + j < Ld) {   // warp-uniform
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) H += __shfl_xor_sync(0xffffffffu, H, o);
+              if (lane == 0) {
+                // relu'(gate) = 0 for gate < 0 (the forward clamps a negative gate to 0)
+                const float live = (P.gate && P.gate[b * (int64_t)Ld + j0 + j] < 0.f) ? 0.f : 1.f;
+                float* gg = P.grad_gate + b * (int64_t)Ld + j0 + j;
+                *gg = (i0 == 0) ? H * live : *gg + H * live;
+              }
+            }
           }
         }
         __syncthreads();
@@ -474,8 +492,20 @@ extern "C" int mmb200_kernel_pool_fwd(const float* q, const float* d, const void
                                       float* score, float* per_kernel, float* per_kernel_query, float* cosine,
                                       int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K, float log_scale,
                                       int32_t mask_dtype, int32_t impl, void* stream_) {
+  return mmb200_kernel_pool_fwd_ex(q, d, q_mask, d_mask, nullptr, mu, sigma, alpha, weight, score, per_kernel,
+                                   per_kernel_query, cosine, B, Lq, Ld, D, K, log_scale, 1e-10f, 0.f, mask_dtype, impl, stream_);
+}
+
+extern "C" int mmb200_kernel_pool_fwd_ex(const float* q, const float* d, const void* q_mask, const void* d_mask,
+                                         const float* doc_gate, const float* mu, const float* sigma, const float* alpha,
+                                         const float* weight, float* score, float* per_kernel, float* per_kernel_query,
+                                         float* cosine, int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K,
+                                         float log_scale, float clamp_min, float score_bias, int32_t mask_dtype,
+                                         int32_t impl, void* stream_) {
   using namespace mmb;
+  MMB_REQUIRE(clamp_min > 0.f, "clamp_min must be positive");
   KpParams P{};
+  P.gate = doc_gate; P.clamp_min = clamp_min; P.bias = score_bias;
   P.q = q; P.d = d; P.q_mask = q_mask; P.d_mask = d_mask; P.mu = mu; P.sigma = sigma; P.alpha = alpha; P.weight = weight;
   P.B = B; P.Lq = Lq; P.Ld = Ld; P.D = D; P.K = K; P.mask_dtype = mask_dtype; P.log_scale = log_scale;
   P.score = score; P.per_kernel = per_kernel; P.per_kernel_query = per_kernel_query; P.cosine = cosine;
@@ -510,8 +540,22 @@ extern "C" int mmb200_kernel_pool_bwd(const float* q, const float* d, const void
                                       float* grad_d, float* grad_alpha, float* grad_weight, float* workspace,
                                       int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K, float log_scale,
                                       int32_t mask_dtype, void* stream_) {
+  return mmb200_kernel_pool_bwd_ex(q, d, q_mask, d_mask, nullptr, mu, sigma, alpha, weight, per_kernel_query, grad_score,
+                                   grad_q, grad_d, nullptr, grad_alpha, grad_weight, workspace, B, Lq, Ld, D, K, log_scale,
+                                   1e-10f, mask_dtype, stream_);
+}
+
+extern "C" int mmb200_kernel_pool_bwd_ex(const float* q, const float* d, const void* q_mask, const void* d_mask,
+                                         const float* doc_gate, const float* mu, const float* sigma, const float* alpha,
+                                         const float* weight, const float* per_kernel_query, const float* grad_score,
+                                         float* grad_q, float* grad_d, float* grad_gate, float* grad_alpha,
+                                         float* grad_weight, float* workspace, int64_t B, int32_t Lq, int32_t Ld,
+                                         int32_t D, int32_t K, float log_scale, float clamp_min, int32_t mask_dtype,
+                                         void* stream_) {
   using namespace mmb;
+  MMB_REQUIRE(clamp_min > 0.f, "clamp_min must be positive");
   KpParams P{};
+  P.gate = doc_gate; P.clamp_min = clamp_min; P.grad_gate = grad_gate;
   P.q = q; P.d = d; P.q_mask = q_mask; P.d_mask = d_mask; P.mu = mu; P.sigma = sigma; P.alpha = alpha; P.weight = weight;
   P.B = B; P.Lq = Lq; P.Ld = Ld; P.D = D; P.K = K; P.mask_dtype = mask_dtype; P.log_scale = log_scale;
   P.S = per_kernel_query; P.grad_score = grad_score; P.grad_q = grad_q; P.grad_d = grad_d;

@@ -19,6 +19,12 @@ struct KpParams {
   int64_t B;
   int32_t Lq, Ld, D, K, mask_dtype;
   float log_scale;
+  // variants of the same pooling: TK-Sparse gates every document term (cikm20_tk_sparse.py:135),
+  // IDCM's ESM clamps at 1e-4 and adds the bias of its Linear(11, 1) (sigir21_idcm.py:185-186)
+  const float* gate;     // [B, Ld] multiplier of the activations of document term j (values < 0 count as 0), or nullptr
+  float clamp_min;       // floor of alpha_k * S_ik before the log (1e-10 in KNRM / TK / TK-Sparse / Conv-KNRM)
+  float bias;            // added to the score
+  float* grad_gate;      // [B, Ld] backward output, or nullptr
   // forward outputs
   float* score;
   float* per_kernel;

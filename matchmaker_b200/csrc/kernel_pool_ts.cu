@@ -47,6 +47,7 @@ constexpr int kOps = 4;               // operand ring: A slot in TMEM (64 column
 constexpr int kAcc = 4;
 constexpr int kAccCols = 64;
 constexpr int kACol0 = kAcc * kAccCols;  // first TMEM column of the A ring
+constexpr int kNormRing = kAcc + kOps + 1;
 constexpr int kDxBytes = 128 * 128;   // [128 rows][32 fp32]
 constexpr int kQxBytes = 32 * 128;    // [32 query rows][32 fp32]
 constexpr int kRawBytes = kDxBytes + kQxBytes;          // 20 KB
@@ -57,7 +58,6 @@ constexpr int kFirstDocWarp = 4, kFirstEpiWarp = 12;
 constexpr int kRegsLight = 56, kRegsConvert = 80, kRegsEpilogue = 128;  // setmaxnreg budgets per warpgroup
 constexpr float kSentinel = 1.0e6f;   // "cosine" of a masked row: ex2(-((1e6 - mu) a)^2) is exactly 0 for any sigma < 1e4
 constexpr float kTinyNorm = 1e-13f;
-constexpr float kClampMin = 1e-10f;
 
 struct KpShared {
   uint64_t raw_full[kMaxRaw];    // TMA -> convert
@@ -68,11 +68,16 @@ struct KpShared {
   uint64_t accempty[kAcc];
   uint32_t tmem_base;
   uint32_t pad;
-  float ss_d[kAcc][2][128];      // |d|^2, one partial per column half (two convert threads per document row)
-  float rs_q[kAcc][32];
+  // |d|^2 (one partial per column half: two convert threads per document row) and 1 / (|q| + eps) travel from the
+  // convert warps to the epilogue in their own ring: the convert warps run up to kOps k-chunks ahead of the MMA warp,
+  // which runs up to kAcc tiles ahead of the epilogue -- kAcc + kOps tiles when a tile is a single k-chunk (D <= 32),
+  // so a ring indexed by the accumulator slot could be overwritten before it is read
+  float ss_d[kNormRing][2][128];
+  float rs_q[kNormRing][32];
   float mu[32], a[32], alpha[32], w[32];
   float pk[32];
   float qm[32];
+  float lg[2][128];              // per cosine tile: log2 of the document-term gate (0 without a gate)
   int live[2][4];                // per cosine tile: last unmasked document row + 1 of each 32-row quarter
 };
 
@@ -219,7 +224,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const int qt = (warp - 2) * 32 + lane;    // 0..63: (query row, column half)
     const int row = qt >> 1, half = qt & 1;
     const int sw = row & 7;
-    int rs_ = 0, os_ = 0, acc = 0;
+    int rs_ = 0, os_ = 0, nr = 0;
     uint32_t rphase = 0, ophase = 0;
     for (int64_t p = p_begin; p < p_end; ++p)
       for (int t = 0; t < tiles; ++t) {
@@ -253,7 +258,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           if (ck == nch - 1) {
             float ss = (ss4.x + ss4.y) + (ss4.z + ss4.w);
             ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-            if (half == 0) S->rs_q[acc][row] = 1.0f / (sqrtf(ss) + kTinyNorm);
+            if (half == 0) S->rs_q[nr][row] = 1.0f / (sqrtf(ss) + kTinyNorm);
           }
           // release the raw slot only after the stores that consumed the loaded values: an arrive placed right after
           // the LDS is hoisted above their completion by ptxas and the TMA overwrites rows that are still being read
@@ -263,7 +268,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           if (++rs_ == n_raw) { rs_ = 0; rphase ^= 1u; }
           if (++os_ == kOps) { os_ = 0; ophase ^= 1u; }
         }
-        if (++acc == kAcc) acc = 0;
+        if (++nr == kNormRing) nr = 0;
       }
     if (PROF && blockIdx.x == 0 && warp == 2 && lane == 0) { prof[6] = pc[0]; prof[7] = pc[1]; }
   } else if (warp < kFirstEpiWarp) {
@@ -273,7 +278,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const int half = (warp - kFirstDocWarp) >> 2;  // which 16 of the chunk's 32 columns
     const int row = qd * 32 + lane;           // document row inside the tile = TMEM lane
     const int sw = row & 7;
-    int rs_ = 0, os_ = 0, acc = 0;
+    int rs_ = 0, os_ = 0, nr = 0;
     uint32_t rphase = 0, ophase = 0;
     for (int64_t p = p_begin; p < p_end; ++p)
       for (int t = 0; t < tiles; ++t) {
@@ -305,7 +310,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             tmem_st_wait();
           }
           if (PROF) pc[2] += clock64() - t_st;
-          if (ck == nch - 1) S->ss_d[acc][half][row] = (ss4.x + ss4.y) + (ss4.z + ss4.w);
+          if (ck == nch - 1) S->ss_d[nr][half][row] = (ss4.x + ss4.y) + (ss4.z + ss4.w);
           // the tcgen05.st above consumed every loaded value and has completed: the raw slot may be refilled and the
           // A slot may be read (an arrive placed right after the LDS would be hoisted above their completion)
           tc_fence_before_sync();
@@ -317,7 +322,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           if (++rs_ == n_raw) { rs_ = 0; rphase ^= 1u; }
           if (++os_ == kOps) { os_ = 0; ophase ^= 1u; }
         }
-        if (++acc == kAcc) acc = 0;
+        if (++nr == kNormRing) nr = 0;
       }
     if (PROF && blockIdx.x == 0 && warp == kFirstDocWarp && lane == 0) { prof[3] = pc[0]; prof[4] = pc[1]; prof[5] = pc[2]; }
   } else {
@@ -328,7 +333,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const int h = ew >> 2;              // which 16 query columns of the 32 this warp extracts in phase A
     const int dmt = P.d_mask ? P.mask_dtype : MMB200_MASK_NONE;
     const int qmt = P.q_mask ? P.mask_dtype : MMB200_MASK_NONE;
-    int acc_slot = 0;
+    int acc_slot = 0, nr = 0;
     uint32_t accphase = 0;
     int64_t tile_seq = 0;
     // kernel centres / widths in registers when they fit (the reference's 11- and 21-kernel models); otherwise they are
@@ -360,16 +365,18 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           tmem_ld_32x32b_x16(taddr + 32 + 16 * h, rl);
           tmem_ld_wait();
           const bool valid = g < P.Ld && mask_test(draw, dmt);
-          const float rsd = 1.0f / (sqrtf(S->ss_d[acc_slot][0][row] + S->ss_d[acc_slot][1][row]) + kTinyNorm);
+          const float rsd = 1.0f / (sqrtf(S->ss_d[nr][0][row] + S->ss_d[nr][1][row]) + kTinyNorm);
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float c = (__uint_as_float(rh[j]) + __uint_as_float(rl[j])) * rsd * S->rs_q[acc_slot][16 * h + j];
+            const float c = (__uint_as_float(rh[j]) + __uint_as_float(rl[j])) * rsd * S->rs_q[nr][16 * h + j];
             v[j] = valid ? c : kSentinel;
           }
           if (h == 0) {  // last live row of this quarter: phase B stops there instead of testing every row
             const uint32_t live = __ballot_sync(0xffffffffu, valid);
             if (lane == 0) S->live[tile_seq & 1][qd] = live ? qd * 32 + 32 - __clz(live) : 0;
+            // gate g_j * exp(-x^2) = 2^(-u^2 + log2 g_j): one exponent term per document row, no extra multiply
+            S->lg[tile_seq & 1][row] = (P.gate && g < P.Ld) ? __log2f(fmaxf(P.gate[p * (int64_t)P.Ld + g], 0.f)) : 0.f;
           }
           tc_fence_before_sync();
           __syncwarp();
@@ -381,6 +388,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           }
         }
         if (++acc_slot == kAcc) { acc_slot = 0; accphase ^= 1u; }
+        if (++nr == kNormRing) nr = 0;
         KP_TIMED(1, named_bar_sync(1, kEpiThreads));
         const long long t_b = PROF ? clock64() : 0;
         {  // phase B: lane = query row; document rows are dealt round-robin to the 8 warps, two at a time (rows r and
@@ -392,16 +400,20 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           auto cos_at = [&](int r) -> float {
             return r < rows_live ? cbuf[r * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)] : kSentinel;
           };
+          const float* lgs = S->lg[tile_seq & 1];
           float c0 = cos_at(ew), c1 = cos_at(ew + 8);
+          float l0 = lgs[ew], l1 = lgs[ew + 8];
           for (int r = ew; r < rows_live; r += 16) {
             const float n0 = cos_at(r + 16), n1 = cos_at(r + 24);
+            const float m0 = lgs[(r + 16) & 127], m1 = lgs[(r + 24) & 127];
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
               const float m = kRegConst ? mu_r[k] : S->mu[k], a = kRegConst ? a_r[k] : S->a[k];
               const float u0 = (c0 - m) * a, u1 = (c1 - m) * a;
-              acc[k] += ex2f(-u0 * u0) + ex2f(-u1 * u1);
+              acc[k] += ex2f(fmaf(-u0, u0, l0)) + ex2f(fmaf(-u1, u1, l1));
             }
             c0 = n0; c1 = n1;
+            l0 = m0; l1 = m1;
           }
         }
         if (PROF) pc[2] += clock64() - t_b;
@@ -421,7 +433,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           float L = 0.f;
           if (k < P.K && lane < P.Lq) {
             if (P.per_kernel_query) P.per_kernel_query[(p * P.Lq + lane) * (int64_t)P.K + k] = Ssum;
-            if (q_live) L = P.log_scale * logf(fmaxf(Ssum * S->alpha[k], kClampMin));
+            if (q_live) L = P.log_scale * logf(fmaxf(Ssum * S->alpha[k], P.clamp_min));
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
@@ -435,7 +447,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         float sc = v * S->w[lane];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
-        if (lane == 0) P.score[p] = sc;
+        if (lane == 0) P.score[p] = sc + P.bias;
       }
       // spart / pk / qm are rewritten only after the next pair's tiles, i.e. after further barriers
     }

@@ -56,6 +56,7 @@ constexpr int kNq = 2 * kMaxLq;           // UMMA N: hi columns 0..39, lo column
 constexpr int kMaxRaw = 6;
 constexpr int kOps = 4;
 constexpr int kAcc = 3;
+constexpr int kNormRing = kAcc + kOps + 1;
 constexpr int kAccCol0 = kOps * 64;       // TMEM: [0, 256) A ring (4 x (32 hi + 32 lo)), [256, 496) 3 accumulators of 80
 constexpr int kDxBytes = 128 * 128;       // [128 rows][32 fp32], rows 0..119 written
 constexpr int kSlotBytes = kChunk * 128;  // one chunk's 40 rows of a k-chunk
@@ -81,8 +82,11 @@ struct TsShared {
   uint64_t accempty[kAcc];
   uint32_t tmem_base;
   uint32_t pad;
-  float ss_d[kAcc][2][128];
-  float rs_q[kAcc][kMaxLq];
+  // norms travel from the convert warps to the epilogue in their own ring: the convert warps run up to kOps k-chunks
+  // ahead of the MMA warp, which runs up to kAcc tiles ahead of the epilogue -- with a single k-chunk per tile
+  // (D <= 32) that is kAcc + kOps tiles, so a ring indexed by the accumulator slot would be overwritten early
+  float ss_d[kNormRing][2][128];
+  float rs_q[kNormRing][kMaxLq];
   float red[kMaxLq];          // sat_emb_reduce1(q_i)
   float qm[kMaxLq];
   float sp[16];
@@ -319,7 +323,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     if (have_work) {
       const int qt = (warp - 2) * 32 + lane;
       const int c = qt & 7, r0 = qt >> 3;
-      int rs_ = 0, os_ = 0, acc = 0;
+      int rs_ = 0, os_ = 0, nr = 0;
       uint32_t rphase = 0, ophase = 0;
       for (; tw.valid(); tw.next()) {
         float ss[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -351,7 +355,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
               v += __shfl_xor_sync(0xffffffffu, v, 1);
               v += __shfl_xor_sync(0xffffffffu, v, 2);
               v += __shfl_xor_sync(0xffffffffu, v, 4);
-              if (c == 0) S->rs_q[acc][r0 + 8 * j] = 1.0f / (sqrtf(v) + kTinyNorm);
+              if (c == 0) S->rs_q[nr][r0 + 8 * j] = 1.0f / (sqrtf(v) + kTinyNorm);
             }
           }
           fence_proxy_async_smem();
@@ -360,7 +364,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           if (++rs_ == n_raw) { rs_ = 0; rphase ^= 1u; }
           if (++os_ == kOps) { os_ = 0; ophase ^= 1u; }
         }
-        if (++acc == kAcc) acc = 0;
+        if (++nr == kNormRing) nr = 0;
       }
     }
   } else if (warp < kFirstEpiWarp) {
@@ -372,7 +376,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const int half = (warp - kFirstDocWarp) >> 2;
       const int row = qd * 32 + lane;
       const int sw = row & 7;
-      int rs_ = 0, os_ = 0, acc = 0;
+      int rs_ = 0, os_ = 0, nr = 0;
       uint32_t rphase = 0, ophase = 0;
       for (; tw.valid(); tw.next()) {
         float4 ss4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -400,7 +404,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             tmem_st_32x32b_x16(taddr + 32, lo);
             tmem_st_wait();
           }
-          if (ck == nch - 1) S->ss_d[acc][half][row] = (ss4.x + ss4.y) + (ss4.z + ss4.w);
+          if (ck == nch - 1) S->ss_d[nr][half][row] = (ss4.x + ss4.y) + (ss4.z + ss4.w);
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) {
@@ -410,7 +414,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           if (++rs_ == n_raw) { rs_ = 0; rphase ^= 1u; }
           if (++os_ == kOps) { os_ = 0; ophase ^= 1u; }
         }
-        if (++acc == kAcc) acc = 0;
+        if (++nr == kNormRing) nr = 0;
       }
     }
   } else {
@@ -437,7 +441,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       float suf[kBlk];
 #pragma unroll
       for (int r = 0; r < kBlk; ++r) suf[r] = 0.f;
-      int acc_slot = 0;
+      int acc_slot = 0, nr = 0;
       uint32_t accphase = 0;
       int cur_doc = -1;
       float qm_i = 0.f;
@@ -511,8 +515,8 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           if (lane == 0) mbar_arrive(&S->accempty[acc_slot]);
           const bool valid = present && mask_test(draw, dmt);
           if (row < kTileRows) {
-            const float rsd = 1.0f / (sqrtf(S->ss_d[acc_slot][0][row] + S->ss_d[acc_slot][1][row]) + kTinyNorm);
-            const float* rq = S->rs_q[acc_slot] + 10 * cg;
+            const float rsd = 1.0f / (sqrtf(S->ss_d[nr][0][row] + S->ss_d[nr][1][row]) + kTinyNorm);
+            const float* rq = S->rs_q[nr] + 10 * cg;
             float v[10];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = valid ? (__uint_as_float(h8[j]) + __uint_as_float(l8[j])) * rsd * rq[j] : kSentinel;
@@ -525,6 +529,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           }
         }
         if (++acc_slot == kAcc) { acc_slot = 0; accphase ^= 1u; }
+        if (++nr == kNormRing) nr = 0;
         named_bar_sync(2, kEpiThreads);
         // ---- token count of the window ending at each pair of this tile (sigir20_tkl.py:210 under "cover") ----
         if (et < kTilePairs) {

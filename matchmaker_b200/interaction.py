@@ -187,12 +187,17 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 def kernel_pool(q: torch.Tensor, d: torch.Tensor, q_mask: torch.Tensor, d_mask: torch.Tensor,
                 mu: torch.Tensor, sigma: torch.Tensor, weight: torch.Tensor, alpha: Optional[torch.Tensor] = None,
                 log_scale: float = 1.0, want_per_kernel: bool = False, want_per_kernel_query: bool = False,
-                want_cosine: bool = False, impl: str = "auto"):
+                want_cosine: bool = False, impl: str = "auto", doc_gate: Optional[torch.Tensor] = None,
+                clamp_min: float = 1e-10, bias: float = 0.0):
     """Cosine match matrix + RBF kernel pooling, forward (knrm.py:52-84 / ecai20_tk.py:105-124).
 
     q [B,Lq,D], d [B,Ld,D] fp32; masks [B,L]; mu/sigma/weight(/alpha) [K].  Returns a dict with "score"
-    [B] and, on request, "per_kernel" [B,K], "per_kernel_query" [B,Lq,K], "cosine" [B,Lq,Ld]."""
-    dev = _require_cuda(q, d, q_mask, d_mask, mu, sigma, weight, alpha)
+    [B] and, on request, "per_kernel" [B,K], "per_kernel_query" [B,Lq,K], "cosine" [B,Lq,Ld].
+
+    Variants: ``doc_gate`` [B,Ld] multiplies every activation of its document term (TK-Sparse,
+    cikm20_tk_sparse.py:135); ``clamp_min`` / ``bias`` are the 1e-4 floor and the Linear bias of IDCM's ESM scorer
+    (sigir21_idcm.py:185-186)."""
+    dev = _require_cuda(q, d, q_mask, d_mask, mu, sigma, weight, alpha, doc_gate)
     if q.dtype != torch.float32 or d.dtype != torch.float32:
         q, d = q.float(), d.float()  # the reference runs TK/KNRM with use_fp16: False (tk.yaml:6)
     q, d = q.contiguous(), d.contiguous()
@@ -208,18 +213,23 @@ def kernel_pool(q: torch.Tensor, d: torch.Tensor, q_mask: torch.Tensor, d_mask: 
     pk = torch.empty((B, K), dtype=torch.float32, device=dev) if want_per_kernel else None
     pkq = torch.empty((B, Lq, K), dtype=torch.float32, device=dev) if want_per_kernel_query else None
     cos = torch.empty((B, Lq, Ld), dtype=torch.float32, device=dev) if want_cosine else None
+    gate = None
+    if doc_gate is not None:
+        gate = _f32c(doc_gate).reshape(B, Ld)
     lib = _lib.load()
     with torch.cuda.device(dev):
-        rc = lib.mmb200_kernel_pool_fwd(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(mu), _ptr(sigma),
-                                        _ptr(alpha), _ptr(weight), _ptr(score), _ptr(pk), _ptr(pkq), _ptr(cos),
-                                        B, Lq, Ld, D, K, float(log_scale), mcode, _IMPLS[impl], _stream(dev))
-    _lib.check(rc, "mmb200_kernel_pool_fwd")
+        rc = lib.mmb200_kernel_pool_fwd_ex(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(gate), _ptr(mu), _ptr(sigma),
+                                           _ptr(alpha), _ptr(weight), _ptr(score), _ptr(pk), _ptr(pkq), _ptr(cos),
+                                           B, Lq, Ld, D, K, float(log_scale), float(clamp_min), float(bias), mcode,
+                                           _IMPLS[impl], _stream(dev))
+    _lib.check(rc, "mmb200_kernel_pool_fwd_ex")
     return {"score": score, "per_kernel": pk, "per_kernel_query": pkq, "cosine": cos}
 
 
 def kernel_pool_bwd(q, d, q_mask, d_mask, mu, sigma, weight, alpha, per_kernel_query, grad_score,
-                    log_scale: float = 1.0):
-    """Backward of :func:`kernel_pool`: returns (grad_q, grad_d, grad_alpha or None, grad_weight)."""
+                    log_scale: float = 1.0, doc_gate: Optional[torch.Tensor] = None, clamp_min: float = 1e-10):
+    """Backward of :func:`kernel_pool`: returns (grad_q, grad_d, grad_alpha or None, grad_weight[, grad_gate when a
+    ``doc_gate`` was given])."""
     dev = _require_cuda(q, d, per_kernel_query, grad_score)
     q, d = q.float().contiguous(), d.float().contiguous()
     B, Lq, D = q.shape
@@ -233,13 +243,18 @@ def kernel_pool_bwd(q, d, q_mask, d_mask, mu, sigma, weight, alpha, per_kernel_q
     ga = torch.empty(K, dtype=torch.float32, device=dev)
     gw = torch.empty(K, dtype=torch.float32, device=dev)
     ws = torch.empty(2 * B * K, dtype=torch.float32, device=dev)
+    gate = None if doc_gate is None else _f32c(doc_gate).reshape(B, Ld)
+    gg = None if doc_gate is None else torch.empty((B, Ld), dtype=torch.float32, device=dev)
     lib = _lib.load()
     with torch.cuda.device(dev):
-        rc = lib.mmb200_kernel_pool_bwd(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(mu), _ptr(sigma),
-                                        _ptr(alpha_c), _ptr(weight), _ptr(per_kernel_query.contiguous()),
-                                        _ptr(_f32c(grad_score)), _ptr(gq), _ptr(gd), _ptr(ga), _ptr(gw), _ptr(ws),
-                                        B, Lq, Ld, D, K, float(log_scale), mcode, _stream(dev))
-    _lib.check(rc, "mmb200_kernel_pool_bwd")
+        rc = lib.mmb200_kernel_pool_bwd_ex(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(gate), _ptr(mu), _ptr(sigma),
+                                           _ptr(alpha_c), _ptr(weight), _ptr(per_kernel_query.contiguous()),
+                                           _ptr(_f32c(grad_score)), _ptr(gq), _ptr(gd), _ptr(gg), _ptr(ga), _ptr(gw),
+                                           _ptr(ws), B, Lq, Ld, D, K, float(log_scale), float(clamp_min), mcode,
+                                           _stream(dev))
+    _lib.check(rc, "mmb200_kernel_pool_bwd_ex")
+    if doc_gate is not None:
+        return gq, gd, (ga if alpha is not None else None), gw, gg
     return gq, gd, (ga if alpha is not None else None), gw
 
 

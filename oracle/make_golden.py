@@ -214,13 +214,68 @@ def golden_bert_dot():
     _save("bert_dot_small", qv=qv, dv=dv, score=score)
 
 
+def golden_tk_sparse():
+    """CIKM20_TK_Sparse (models/published/cikm20_tk_sparse.py): full forward of the reference class; the fixture keeps the
+    tensors that enter the interaction stage (contextualised embeddings + the learned document-term gate)."""
+    torch.manual_seed(103)
+    emb, heads, layers, proj, ff, max_len = 40, 4, 1, 16, 32, 64
+    mu = [1.0, 0.9, 0.7, 0.5, 0.3, 0.1, -0.1, -0.3, -0.5, -0.7, -0.9]
+    sigma = [0.1] * 11
+    ref = R.load_tk_sparse(emb, mu, sigma, heads, layers, proj, ff, max_len, True)
+    ref.eval()
+    with torch.no_grad():
+        ref.kernel_alpha_scaler.copy_(torch.rand_like(ref.kernel_alpha_scaler) + 0.5)
+        ref.stop_word_reducer2.bias.fill_(0.3)     # so that relu() closes the gate for a share of the document terms
+    B, Lq, Ld = 6, 12, 48
+    q, d, qm, dm = O.synth_kernel_pool_inputs(B, Lq, Ld, emb, seed=2100)
+    with torch.no_grad():
+        score, sec, stop = ref.forward(q, d, qm, dm, output_secondary_output=True)
+        score_plain, stop_plain = ref.forward(q, d, qm, dm)
+        q_ctx, _ = ref.forward_representation(q, qm, ref.positional_features_q[:, :Lq, :])
+        d_ctx, _ = ref.forward_representation(d, dm, ref.positional_features_d[:, :Ld, :])
+    assert torch.equal(score, score_plain) and torch.equal(stop, stop_plain)
+    gate = stop.squeeze(1)
+    assert 0.05 < float((gate[dm.bool()] == 0).float().mean()) < 0.95, "the fixture should contain closed and open gates"
+    w = ref.kernel_bin_weights.weight.detach().view(-1)
+    alpha = ref.kernel_alpha_scaler.detach().view(-1)
+    o_score, o_sec = O.kernel_pool_tk_sparse(q_ctx, d_ctx, qm, dm, gate, ref.mu.view(-1), ref.sigma.view(-1), alpha, w)
+    _check(o_score, score, "tk_sparse score", rtol=1e-5, atol=1e-6)
+    _check(o_sec["per_kernel"], sec["per_kernel"], "tk_sparse per_kernel", rtol=1e-5, atol=1e-5)
+    state = {"sd__" + k: v for k, v in ref.state_dict().items()}
+    _save("tk_sparse", q=q, d=d, q_mask=qm, d_mask=dm, q_ctx=q_ctx, d_ctx=d_ctx, doc_gate=gate, mu=ref.mu.view(-1),
+          sigma=ref.sigma.view(-1), alpha=alpha, weight=w, score=score, per_kernel=sec["per_kernel"],
+          document_stop_words=stop, cfg=np.array([emb, heads, layers, proj, ff, max_len]), **state)
+
+
+def golden_conv_knrm():
+    """Conv_KNRM (models/conv_knrm.py): full forward of the reference class + the n-gram tensors between the
+    convolutions and the 3 x 3 cross-match."""
+    torch.manual_seed(104)
+    emb, n_grams, K, conv_out = 24, 3, 11, 32
+    ref = R.load_conv_knrm(emb, n_grams, K, conv_out)
+    ref.eval()
+    B, Lq, Ld = 5, 9, 40
+    q, d, qm, dm = O.synth_kernel_pool_inputs(B, Lq, Ld, emb, seed=2200)
+    with torch.no_grad():
+        score = ref.forward(q, d, qm, dm)
+        qg = [c(q.transpose(1, 2)).transpose(1, 2) for c in ref.convolutions]
+        dg = [c(d.transpose(1, 2)).transpose(1, 2) for c in ref.convolutions]
+    o_score, o_all = O.conv_knrm_cross_match(qg, dg, qm, dm, ref.mu.view(-1), ref.sigma.view(-1), ref.dense.weight.view(-1))
+    _check(o_score, score, "conv_knrm score")
+    state = {"sd__" + k: v for k, v in ref.state_dict().items()}
+    _save("conv_knrm", q=q, d=d, q_mask=qm, d_mask=dm, mu=ref.mu.view(-1), sigma=ref.sigma.view(-1),
+          dense_weight=ref.dense.weight.detach().view(-1), score=score, all_grams=o_all,
+          cfg=np.array([emb, n_grams, K, conv_out]),
+          **{f"qg{i}": t for i, t in enumerate(qg)}, **{f"dg{i}": t for i, t in enumerate(dg)}, **state)
+
+
 def main():
     if not R.reference_available():
         print("reference not mounted at", R.REFERENCE_ROOT, "- cannot regenerate golden vectors", file=sys.stderr)
         return 1
     only = set(sys.argv[1:])   # e.g. `python -m oracle.make_golden knrm` regenerates one family
     for name, fn in (("knrm", golden_knrm), ("tk", golden_tk), ("tkl", golden_tkl), ("colbert", golden_colbert),
-                     ("bert_dot", golden_bert_dot)):
+                     ("bert_dot", golden_bert_dot), ("tk_sparse", golden_tk_sparse), ("conv_knrm", golden_conv_knrm)):
         if not only or name in only:
             fn()
     return 0
