@@ -19,11 +19,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
-// Watchdog for every spin-wait in the kernels: a protocol bug must end in a trap (the launch
-// fails with an error the host reports) instead of a hung GPU.
-#ifndef MMB_WATCHDOG_CYCLES
-#define MMB_WATCHDOG_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz
-#endif
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier
@@ -69,11 +64,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Blocking wait.  Every try_wait parks the warp (suspend hint above) until the phase completes or something wakes it;
+// the watchdog counts wake-ups instead of reading the clock (3 instructions per turn instead of 6: roles that wait on
+// a slower role share their scheduler with it): 2^24 futile wake-ups -- seconds of waiting, no protocol in this library
+// waits milliseconds -- end in a trap, so a protocol bug fails the launch instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > MMB_WATCHDOG_CYCLES) {
+    if (++spins > (1u << 24)) {
       printf("mmb200: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
       __trap();
