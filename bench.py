@@ -607,6 +607,37 @@ def _roofline(wl, kern_ms, workload_key):
     return roof
 
 
+def graphed_step(fn, dev):
+    """Capture one step (a handful of short launches: with a Python caller the host issues them more slowly than the GPU
+    retires them) into a CUDA graph and return a replay closure; None if the step cannot be captured.  The kernels, their
+    arguments and their order are those of the eager step; only the launch path changes."""
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = fn()
+        g.replay()
+        torch.cuda.synchronize(dev)
+
+        def replay():
+            g.replay()
+            return out
+        return replay
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write("bench: CUDA-graph capture of the step failed (%r); running it eagerly\n" % (e,))
+        try:
+            torch.cuda.synchronize(dev)
+        except Exception:  # noqa: BLE001
+            pass
+        return None
+
+
 def bench_secondary(name, dev, steps, cpu_budget_s):
     """One sub-record per secondary BASELINE config, measured inside the default run at N=1 so that the driver's run
     times every workload, not only the headline one: value (HBM-resident, CUDA events), roofline, e2e, CPU port."""
@@ -615,10 +646,13 @@ def bench_secondary(name, dev, steps, cpu_budget_s):
     for _ in range(3):
         wl.kernel_step()
     torch.cuda.synchronize()
+    step = graphed_step(wl.kernel_step, dev) if wl.launches_per_step > 1 else None
+    graphed = step is not None
+    step = step or wl.kernel_step
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        wl.kernel_step()
+        step()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -632,7 +666,7 @@ def bench_secondary(name, dev, steps, cpu_budget_s):
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / n_e2e
     rec = {"metric": wl.metric, "value": wl.pairs / (ms * 1e-3), "unit": "pairs/s", "steps": steps, "ms_per_step": ms,
-           "dtype": wl.dtype, "config": wl.config(1), "roofline": _roofline(wl, ms, name),
+           "dtype": wl.dtype, "config": dict(wl.config(1), cuda_graph=graphed), "roofline": _roofline(wl, ms, name),
            "gpu_launches": steps * wl.launches_per_step,
            "e2e": {"value": wl.pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": out.numel() * out.element_size(), "ms_per_step": e2e_s * 1e3, "note": wl.e2e_note}}
@@ -650,6 +684,7 @@ def main():
     ap.add_argument("--workload", default="colbert", choices=WORKLOADS)
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: min(steps, 5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="never replay the step from a CUDA graph")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the per-workload sub-records (tk, knrm, tkl, bert_dot, ...) of the default N=1 run")
     args = ap.parse_args()
@@ -710,6 +745,12 @@ def main():
     if world > 1:
         torch.cuda.current_stream().wait_stream(side)
     sync_all()
+    kstep = wl.kernel_step
+    graphed = False
+    if world == 1 and wl.launches_per_step > 1 and not args.no_graph:
+        g = graphed_step(wl.kernel_step, dev)
+        if g is not None:
+            kstep, graphed = g, True
 
     # ---- timed region: `value` (inputs resident in HBM) -----------------------------------------
     sampler = ClockSampler(local_rank)
@@ -722,7 +763,7 @@ def main():
     e0.record()
     for i in range(args.steps):
         kern_ev[i][0].record()
-        out = wl.kernel_step()
+        out = kstep()
         kern_ev[i][1].record()
         if world > 1:
             exchange_async(out)
@@ -763,7 +804,7 @@ def main():
     if rank == 0:
         line = {"metric": wl.metric, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(world),
+                "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": dict(wl.config(world), cuda_graph=graphed),
                 "clocks": clocks,
                 "e2e": {"value": pairs_per_step / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "note": wl.e2e_note},

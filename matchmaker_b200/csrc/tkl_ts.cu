@@ -16,14 +16,14 @@
 // starts inside a document first replays the previous tile's last block -- its "halo" -- to rebuild the suffix sums).
 // Windows outside every share are exactly 0 and come from one cudaMemsetAsync.
 //
-// Per CTA (896 threads = 7 warpgroups, registers re-dealt with setmaxnreg), same operand pipeline as
+// Per CTA (768 threads = 6 warpgroups, registers re-dealt with setmaxnreg), same operand pipeline as
 // kernel_pool_ts.cu (x = hi + lo with hi = x & 0xffffe000; [Qhi;Qlo] stacked along the UMMA N dimension, the
 // document operand written to TENSOR MEMORY by the convert warps):
 //   warp 0      TMA producer: per 32-column k-chunk up to three [40 x 32] chunk boxes + one [40 x 32] query box
 //   warp 1      tcgen05.mma kind::tf32, M = 128 (120 used), N = 80 = [40 hi | 40 lo], A from TMEM, 3 accumulators
 //   warps 2-3   query convert (hi / lo B operand, query norms)
-//   warps 4-11  document convert, two threads per position (hi / lo straight into TMEM, position norms)
-//   warps 12-27 epilogue.  Phase A: thread = position, 10 query columns per warp: cosine tile to shared memory (masked
+//   warps 4-7   document convert, one thread per position (hi / lo straight into TMEM, position norms)
+//   warps 8-23  epilogue.  Phase A: thread = position, 10 query columns per warp: cosine tile to shared memory (masked
 //               positions -> a sentinel whose activations are exactly 0).  Phase B: thread = (query row i, kernel k),
 //               walks the tile's 60 pairs in registers: activation pair sums, block prefix / suffix, window sum,
 //               saturation (per-document table indexed by the window's token count), w_k * T; a 16-value transposed
@@ -46,7 +46,7 @@ namespace mmb {
 
 namespace {
 
-constexpr int kThreads = 896;
+constexpr int kThreads = 768;
 constexpr int kChunk = 40, kWindow = 30;
 constexpr int kTileSlots = 3, kTileRows = kTileSlots * kChunk;   // 120 positions
 constexpr int kTilePairs = kTileRows / 2;                       // 60
@@ -64,9 +64,9 @@ constexpr int kQxBytes = kMaxLq * 128;
 constexpr int kRawBytes = kDxBytes + kQxBytes;   // 21 KB
 constexpr int kQopBytes = kNq * 128;      // B operand: rows 0-39 Q hi, rows 40-79 Q lo
 constexpr int kEpiWarps = 16, kEpiThreads = kEpiWarps * 32;
-constexpr int kFirstDocWarp = 4, kFirstEpiWarp = 12;
-constexpr int kReleaseArrivals = 8 + 64;
-constexpr int kRegsLight = 56, kRegsConvert = 64, kRegsEpilogue = 80;
+constexpr int kFirstDocWarp = 4, kFirstEpiWarp = 8;
+constexpr int kReleaseArrivals = 4 + 64;   // lane 0 of each document convert warp + every lane of the two query warps
+constexpr int kRegsLight = 56, kRegsConvert = 104, kRegsEpilogue = 88;   // 128 x 56 + 128 x 104 + 512 x 88 = 64 K registers
 constexpr int kCsStride = 44;             // floats per cosine-tile row (11 16-byte units: conflict-free 16-byte row writes)
 constexpr int kSatStride = 33;            // table row stride (token counts 0..30)
 constexpr float kSentinel = 1.0e6f;
@@ -85,7 +85,7 @@ struct TsShared {
   // norms travel from the convert warps to the epilogue in their own ring: the convert warps run up to kOps k-chunks
   // ahead of the MMA warp, which runs up to kAcc tiles ahead of the epilogue -- with a single k-chunk per tile
   // (D <= 32) that is kAcc + kOps tiles, so a ring indexed by the accumulator slot would be overwritten early
-  float ss_d[kNormRing][2][128];
+  float ss_d[kNormRing][128];
   float rs_q[kNormRing][kMaxLq];
   float red[kMaxLq];          // sat_emb_reduce1(q_i)
   float qm[kMaxLq];
@@ -122,34 +122,43 @@ __global__ void __launch_bounds__(1024) tkl_plan_kernel(const int32_t* __restric
                                                         const float* __restrict__ mu, const float* __restrict__ sigma, int K,
                                                         int force_cover, int32_t* __restrict__ plan) {
   __shared__ int sums[1024];
-  const int t = threadIdx.x;
-  const int64_t per = (B + 1023) / 1024;
-  const int64_t b0 = min(B, (int64_t)t * per), b1 = min(B, b0 + per);
+  __shared__ int carry;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tiles_max = (C + kTileSlots - 1) / kTileSlots;
-  auto tiles_of = [&](int64_t b) {
+  // pass 1: tiles of every document (one warp per document, coalesced reads of its C slots) -> plan[2 + b]
+  for (int64_t b = warp; b < B; b += 32) {
     int c_last = -1;
-    for (int c = C - 1; c >= 0; --c)
-      if (slot_to_packed[b * C + c] >= 0) { c_last = c; break; }
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + lane;
+      const bool packed = c < C && slot_to_packed[b * C + c] >= 0;
+      const unsigned m = __ballot_sync(0xffffffffu, packed);
+      if (m) c_last = c0 + 31 - __clz(m);
+    }
     // windows overlapping a packed chunk end at the latest in slot c_last + 1
-    return c_last < 0 ? 0 : min(tiles_max, (c_last + 1) / kTileSlots + 1);
-  };
-  int local = 0;
-  for (int64_t b = b0; b < b1; ++b) local += tiles_of(b);
-  sums[t] = local;
+    if (lane == 0) plan[2 + b] = c_last < 0 ? 0 : min(tiles_max, (c_last + 1) / kTileSlots + 1);
+  }
+  if (t == 0) carry = 0;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {  // inclusive scan
-    const int v = t >= o ? sums[t - o] : 0;
+  // pass 2: exclusive prefix sums in place, 1024 documents per round
+  for (int64_t base = 0; base < B; base += 1024) {
+    const int64_t b = base + t;
+    const int v = b < B ? plan[2 + b] : 0;
+    sums[t] = v;
     __syncthreads();
-    sums[t] += v;
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int u = t >= o ? sums[t - o] : 0;
+      __syncthreads();
+      sums[t] += u;
+      __syncthreads();
+    }
+    if (b < B) plan[2 + b] = carry + sums[t] - v;
+    __syncthreads();
+    if (t == 1023) carry += sums[1023];
     __syncthreads();
   }
-  int run = sums[t] - local;
-  for (int64_t b = b0; b < b1; ++b) {
-    plan[2 + b] = run;
-    run += tiles_of(b);
-  }
-  if (t == 1023) { plan[1] = sums[1023]; plan[2 + B] = sums[1023]; }
   if (t == 0) {
+    plan[1] = carry;
+    plan[2 + B] = carry;
     // activation k is non-zero (ex2.approx.ftz) for |c - mu_k| * a_k <= sqrt(126); 11.0 leaves a margin.  Sweep the
     // union of the intervals over [-1.01, 1.01].
     float x = -1.01f;
@@ -369,42 +378,51 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
   } else if (warp < kFirstEpiWarp) {
     // ------------------------------- document convert ---------------------------
-    setmaxnreg_dec<kRegsConvert>();
+    // one thread per position (TMEM lane): this kernel is bound by the SM's issue slots (ncu: 65 % issue-active, the
+    // MUFU-heavy epilogue next door), not by the latency of the convert chain, so the per-chunk bookkeeping (barrier
+    // waits, address arithmetic, arrivals) is paid by 4 warps instead of 8
+    setmaxnreg_inc<kRegsConvert>();
     TKL_WALK();
     if (have_work) {
       const int qd = warp & 3;
-      const int half = (warp - kFirstDocWarp) >> 2;
       const int row = qd * 32 + lane;
       const int sw = row & 7;
+      const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16);
       int rs_ = 0, os_ = 0, nr = 0;
       uint32_t rphase = 0, ophase = 0;
       for (; tw.valid(); tw.next()) {
         float4 ss4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int ck = 0; ck < nch; ++ck) {
-          const bool active = half == 0 || P.D - ck * 32 > 16;   // these 16 columns hold data (warp-uniform)
+          const bool second = P.D - ck * 32 > 16;   // columns 16..31 of this chunk hold data (warp-uniform)
           mbar_wait(&S->raw_full[rs_], rphase);
           const uint8_t* xrow = raws + (size_t)rs_ * kRawBytes + row * 128;
-          float4 x[4];
+          float4 x[8];
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            x[c] = active ? *reinterpret_cast<const float4*>(xrow + (((4 * half + c) ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c = 0; c < 8; ++c)
+            x[c] = (c < 4 || second) ? *reinterpret_cast<const float4*>(xrow + ((c ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 8; ++c) {
             const float4 v = x[c];
             ss4.x = fmaf(v.x, v.x, ss4.x); ss4.y = fmaf(v.y, v.y, ss4.y); ss4.z = fmaf(v.z, v.z, ss4.z); ss4.w = fmaf(v.w, v.w, ss4.w);
           }
           mbar_wait(&S->op_empty[os_], ophase ^ 1u);
           tc_fence_after_sync();
-          if (active) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(os_ * 64 + 16 * half);
+          {
+            const uint32_t taddr = trow + (uint32_t)(os_ * 64);
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int c = 0; c < 4; ++c) split4(x[c], hi + 4 * c, lo + 4 * c);
             tmem_st_32x32b_x16(taddr, hi);
             tmem_st_32x32b_x16(taddr + 32, lo);
+            if (second) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) split4(x[4 + c], hi + 4 * c, lo + 4 * c);
+              tmem_st_32x32b_x16(taddr + 16, hi);
+              tmem_st_32x32b_x16(taddr + 48, lo);
+            }
             tmem_st_wait();
           }
-          if (ck == nch - 1) S->ss_d[nr][half][row] = (ss4.x + ss4.y) + (ss4.z + ss4.w);
+          if (ck == nch - 1) S->ss_d[nr][row] = (ss4.x + ss4.y) + (ss4.z + ss4.w);
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) {
@@ -515,7 +533,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           if (lane == 0) mbar_arrive(&S->accempty[acc_slot]);
           const bool valid = present && mask_test(draw, dmt);
           if (row < kTileRows) {
-            const float rsd = 1.0f / (sqrtf(S->ss_d[nr][0][row] + S->ss_d[nr][1][row]) + kTinyNorm);
+            const float rsd = 1.0f / (sqrtf(S->ss_d[nr][row]) + kTinyNorm);
             const float* rq = S->rs_q[nr] + 10 * cg;
             float v[10];
 #pragma unroll
@@ -684,11 +702,19 @@ int tkl_window_ts_launch(TklParams& P, const DeviceInfo& dev, cudaStream_t strea
   MMB_CHECK_CUDA(cudaMemsetAsync(P.window_score, 0, (size_t)P.B * P.W * sizeof(float), stream));
   const int grid = dev.sm_count;
   const int fallback = P.segs > 0 ? 1 : 0;
+  static bool attr_set[2][64] = {};
+  const int di = dev.device & 63;
   if (P.saturation == 0) {
-    MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!attr_set[0][di]) {
+      MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev.max_smem_optin));
+      attr_set[0][di] = true;
+    }
     tkl_ts_kernel<0><<<grid, kThreads, smem, stream>>>(tq, tc, P, n_raw, fallback);
   } else {
-    MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!attr_set[1][di]) {
+      MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev.max_smem_optin));
+      attr_set[1][di] = true;
+    }
     tkl_ts_kernel<1><<<grid, kThreads, smem, stream>>>(tq, tc, P, n_raw, fallback);
   }
   MMB_CHECK_CUDA(cudaGetLastError());

@@ -43,3 +43,6 @@ timed("window scores (tcgen05)", lambda: win("tcgen05"))
 timed("window scores (simt)", lambda: win("simt"), n=5)
 timed("top hills", lambda: interaction.tkl_top_hills(ws_holder["ws"], c["cs"]))
 timed("full step", wl.kernel_step)
+g = bench.graphed_step(wl.kernel_step, dev)
+if g is not None:
+    timed("full step (CUDA graph replay)", g)
