@@ -326,6 +326,66 @@ class KernelPoolWorkload:
                 "l2_policy": "inputs larger than L2 (%.2f GB per GPU per step)" % (self.alg_bytes / 1e9)}
 
 
+class KernelPoolTrainWorkload(KernelPoolWorkload):
+    """TK interaction forward + backward (what train.py:504,526 runs per step through autograd): scores, then gradients
+    to both embedding tensors, alpha and the bin weights.  Algorithmic bytes per pair: the forward
+    reads q, d, masks; the backward reads them again plus S [Lq, K] and writes dq, dd."""
+    launches_per_step = 3   # forward, backward, batch reduction of d weight / d alpha
+    graph_ok = False        # the step runs through torch.autograd
+
+    def __init__(self, rank, dev):
+        super().__init__(rank, dev, "tk")
+        self.name = "tk_kernel_pool_train"
+        self.B = self.pairs = 1024
+        self.q, self.d, self.qm, self.dm = self.q[:self.B], self.d[:self.B], self.qm[:self.B], self.dm[:self.B]
+        self.metric = "query-doc pairs/sec (TK cosine + RBF kernel pooling forward + backward, D=300)"
+        self.kernel = "kernel_pool_ts_kernel + kernel_pool_bwd_simt"
+        fwd = (self.Lq + self.Ld) * self.D * 4 + (self.Lq + self.Ld) * 4 + 4
+        bwd = fwd + self.Lq * 21 * 4 * 2 + (self.Lq + self.Ld) * self.D * 4
+        self.alg_bytes = (fwd + bwd) * self.B
+        self.alg_note = "forward %d B/pair + backward %d B/pair (inputs re-read, S saved and re-read, dq/dd written)" % (fwd, bwd)
+
+    def to_device(self):
+        super().to_device()
+        self.c[0].requires_grad_(True)
+        self.c[1].requires_grad_(True)
+        self.c[6].requires_grad_(True)
+        self.calpha.requires_grad_(True)
+        self.gout = torch.ones(self.B, device=self.dev)
+
+    def kernel_step(self):
+        from matchmaker_b200 import autograd
+        for t in (self.c[0], self.c[1], self.c[6], self.calpha):
+            t.grad = None
+        score, _ = autograd.kernel_pool(self.c[0], self.c[1], self.c[2], self.c[3], self.c[4], self.c[5], self.c[6], self.calpha,
+                                        self.log_scale)
+        score.backward(self.gout)
+        return self.c[0].grad
+
+    def e2e_step(self):
+        from matchmaker_b200 import autograd
+        dq, dd, dqm, ddm = [t.to(self.dev, non_blocking=True) for t in self.h]
+        dq.requires_grad_(True)
+        dd.requires_grad_(True)
+        score, _ = autograd.kernel_pool(dq, dd, dqm, ddm, self.c[4], self.c[5], self.c[6].detach(), self.calpha.detach(), self.log_scale)
+        score.backward(self.gout)
+        return torch.cat([score.detach().cpu(), dq.grad.sum().view(1).cpu()])
+
+    e2e_note = "pinned host embeddings+masks -> H2D -> forward + backward kernels -> D2H scores (+ a gradient checksum)"
+
+    def cpu_prepare(self):
+        self.cpu_n = 64
+
+    def cpu_step(self):
+        from oracle import interaction_oracle as O
+        n = self.cpu_n
+        q = self.q[:n].clone().requires_grad_(True)
+        d = self.d[:n].clone().requires_grad_(True)
+        s = O.kernel_pool_tk(q, d, self.qm[:n], self.dm[:n], self.mu, self.sigma, self.alpha, self.w)[0]
+        s.sum().backward()
+        return q.grad
+
+
 class TklWorkload:
     """BASELINE config 5: TKL interaction + window pooling, Lq=40, Ld=2000, D=300, 11 kernels, 16 docs per GPU
     (128 over 8 GPUs); op-level inputs = contextualised query + packed contextualised chunks."""
@@ -480,8 +540,8 @@ class BertDotWorkload:
                 "l2_policy": "passage shard 1.69 GB per GPU, larger than L2"}
 
 
-WORKLOADS = ["colbert", "tk", "knrm", "tkl", "bert_dot"]
-SECONDARY = ["tk", "knrm", "tkl", "bert_dot"]
+WORKLOADS = ["colbert", "tk", "knrm", "tkl", "bert_dot", "tk_train"]
+SECONDARY = ["tk", "knrm", "tkl", "bert_dot", "tk_train"]
 
 
 def make_workload(name, rank, dev):
@@ -489,6 +549,8 @@ def make_workload(name, rank, dev):
         return ColbertWorkload(rank, dev)
     if name in ("tk", "knrm"):
         return KernelPoolWorkload(rank, dev, name)
+    if name == "tk_train":
+        return KernelPoolTrainWorkload(rank, dev)
     if name == "tkl":
         return TklWorkload(rank, dev)
     if name == "bert_dot":
@@ -646,7 +708,7 @@ def bench_secondary(name, dev, steps, cpu_budget_s):
     for _ in range(3):
         wl.kernel_step()
     torch.cuda.synchronize()
-    step = graphed_step(wl.kernel_step, dev) if wl.launches_per_step > 1 else None
+    step = graphed_step(wl.kernel_step, dev) if (wl.launches_per_step > 1 and getattr(wl, "graph_ok", True)) else None
     graphed = step is not None
     step = step or wl.kernel_step
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -747,7 +809,7 @@ def main():
     sync_all()
     kstep = wl.kernel_step
     graphed = False
-    if world == 1 and wl.launches_per_step > 1 and not args.no_graph:
+    if world == 1 and wl.launches_per_step > 1 and getattr(wl, "graph_ok", True) and not args.no_graph:
         g = graphed_step(wl.kernel_step, dev)
         if g is not None:
             kstep, graphed = g, True

@@ -88,6 +88,10 @@ __device__ __forceinline__ int64_t pair_dmask_row_of(const MaxsimParams& P, int6
   return P.pair_d ? (int64_t)P.pair_d[p] : p;
 }
 
+// kArgmax: the training instantiation also tracks WHICH document row won each query token's max (what backward needs,
+// matchmaker/models/colbert.py:71 through autograd): a compare + two selects per accumulator element instead of a third
+// of an FMNMX3 -- ~9x the epilogue instructions, still a fraction of the ~2000 cycles a document's bytes take to arrive.
+template <bool kArgmax>
 __global__ void __launch_bounds__(kThreads, 1)
 maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
                  const __grid_constant__ CUtensorMap tmap_d16, MaxsimParams P, QmLaunch L) {
@@ -300,6 +304,7 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       uint64_t qraw = 0;
       if (lane < P.Lq) qraw = (qmt != MMB200_MASK_NONE) ? mask_raw(P.q_mask, qmt, qi * (int64_t)P.Lq + lane) : 1;
       float m = -INFINITY;
+      int am = -1;   // row of the running maximum (first one on ties); stays -1 when nothing beats -inf
       for (int t = 0; t < L.tiles; ++t) {
         const int64_t u = n * L.tiles + t;  // tile sequence number inside this CTA
         const int acc = (int)(u % L.acc_slots);
@@ -311,6 +316,17 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
           tmem_ld_wait();
+          if constexpr (kArgmax) {
+            const int col0 = t * L.tn + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]);
+              const bool gt = v > m;
+              m = gt ? v : m;
+              am = gt ? col0 + j : am;
+            }
+            continue;
+          }
           float a = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
           float b = max3(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]));
 #pragma unroll
@@ -325,12 +341,28 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           uint32_t r[16];
           tmem_ld_32x32b_x16(taddr + n32 * 32, r);
           tmem_ld_wait();
+          if constexpr (kArgmax) {
+            const int col0 = t * L.tn + n32 * 32;
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) m = max3(m, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+            for (int j = 0; j < 16; ++j) {
+              const float v = __uint_as_float(r[j]);
+              const bool gt = v > m;
+              m = gt ? v : m;
+              am = gt ? col0 + j : am;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) m = max3(m, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+          }
         }
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&S->accempty[acc]);
+      }
+      if constexpr (kArgmax) {
+        // rows >= Ld are the -inf padding and the virtual -1000 row: a max taken there carries no gradient (-1), like a
+        // masked query token
+        if (lane < P.Lq) P.argmax[p * (int64_t)P.Lq + lane] = (mask_test(qraw, qmt) && am < P.Ld) ? am : -1;
       }
       float total = mask_test(qraw, qmt) ? m : 0.f;  // lanes >= Lq carry qraw = 0
 #pragma unroll
@@ -377,7 +409,7 @@ int maxsim_rows_needed_launch(const void* d_mask, int mask_dtype, int32_t* rows_
 int maxsim_qm_launch(const MaxsimParams& P, int dtype, const DeviceInfo& dev, cudaStream_t stream, bool* handled) {
   *handled = false;
   if (dtype != MMB200_F16 && dtype != MMB200_BF16) return MMB200_OK;
-  if (P.Lq > kQRows || (P.dim != 64 && P.dim != 128) || P.argmax) return MMB200_OK;
+  if (P.Lq > kQRows || (P.dim != 64 && P.dim != 128)) return MMB200_OK;
   if (P.rows_needed && (P.pair_d || P.pair_dmask)) return MMB200_OK;  // rows_needed is indexed by the implicit doc id
   if ((reinterpret_cast<uintptr_t>(P.q) | reinterpret_cast<uintptr_t>(P.d)) & 15) return MMB200_OK;
   QmLaunch L;
@@ -427,8 +459,13 @@ int maxsim_qm_launch(const MaxsimParams& P, int dtype, const DeviceInfo& dev, cu
   }
   *handled = true;
   const int grid = (int)std::min<int64_t>(dev.sm_count, P.n_pairs);
-  MMB_CHECK_CUDA(cudaFuncSetAttribute(maxsim_qm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  maxsim_qm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tq, td, td16, P, L);
+  if (P.argmax) {
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(maxsim_qm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    maxsim_qm_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(tq, td, td16, P, L);
+  } else {
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(maxsim_qm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    maxsim_qm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tq, td, td16, P, L);
+  }
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;
 }

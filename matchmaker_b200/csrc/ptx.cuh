@@ -51,7 +51,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // instead of returning at once, so a role that waits for a slower one does not burn the SM's issue slots on a
 // try_wait / branch loop (ncu on tkl_ts_kernel: the convert warps, waiting on the epilogue-bound pipeline, executed
 // 30 % of all warp instructions before this hint was added).
-constexpr uint32_t kMbarSuspendHintNs = 0x989680u;  // 10 ms: upper bound only, the wait ends when the phase completes
+constexpr uint32_t kMbarSuspendHintNs = 50000u;  // 50 us: upper bound of one nap, the wait ends when the phase completes
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -66,13 +66,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 
 // Blocking wait.  Every try_wait parks the warp (suspend hint above) until the phase completes or something wakes it;
 // the watchdog counts wake-ups instead of reading the clock (3 instructions per turn instead of 6: roles that wait on
-// a slower role share their scheduler with it): 2^24 futile wake-ups -- seconds of waiting, no protocol in this library
-// waits milliseconds -- end in a trap, so a protocol bug fails the launch instead of hanging the GPU.
+// a slower role share their scheduler with it): 2^18 futile wake-ups (13 s of naps in a true deadlock, milliseconds of back-to-back wake-ups; no protocol here
+// waits that long) end in a trap, so a protocol bug fails the launch instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
+    if (++spins > (1u << 18)) {
       printf("mmb200: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
       __trap();

@@ -66,7 +66,9 @@ constexpr int kQopBytes = kNq * 128;      // B operand: rows 0-39 Q hi, rows 40-
 constexpr int kEpiWarps = 16, kEpiThreads = kEpiWarps * 32;
 constexpr int kFirstDocWarp = 4, kFirstEpiWarp = 8;
 constexpr int kReleaseArrivals = 4 + 64;   // lane 0 of each document convert warp + every lane of the two query warps
-constexpr int kRegsLight = 56, kRegsConvert = 104, kRegsEpilogue = 88;   // 128 x 56 + 128 x 104 + 512 x 88 = 64 K registers
+// The re-deal must fit the registers the CTA was LAUNCHED with (768 threads x 80 = 61 440), not the SM's 64 K: a
+// setmaxnreg.inc beyond that pool never returns.  Only the light warpgroup gives registers back; the others keep 80.
+constexpr int kRegsLight = 56;   // convert and epilogue warps keep the 80 registers of the launch
 constexpr int kCsStride = 44;             // floats per cosine-tile row (11 16-byte units: conflict-free 16-byte row writes)
 constexpr int kSatStride = 33;            // table row stride (token counts 0..30)
 constexpr float kSentinel = 1.0e6f;
@@ -381,7 +383,6 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     // one thread per position (TMEM lane): this kernel is bound by the SM's issue slots (ncu: 65 % issue-active, the
     // MUFU-heavy epilogue next door), not by the latency of the convert chain, so the per-chunk bookkeeping (barrier
     // waits, address arithmetic, arrivals) is paid by 4 warps instead of 8
-    setmaxnreg_inc<kRegsConvert>();
     TKL_WALK();
     if (have_work) {
       const int qd = warp & 3;
@@ -396,32 +397,39 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           const bool second = P.D - ck * 32 > 16;   // columns 16..31 of this chunk hold data (warp-uniform)
           mbar_wait(&S->raw_full[rs_], rphase);
           const uint8_t* xrow = raws + (size_t)rs_ * kRawBytes + row * 128;
-          float4 x[8];
+          float4 x[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            x[c] = (c < 4 || second) ? *reinterpret_cast<const float4*>(xrow + ((c ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c = 0; c < 4; ++c) x[c] = *reinterpret_cast<const float4*>(xrow + ((c ^ sw) << 4));
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < 4; ++c) {
             const float4 v = x[c];
             ss4.x = fmaf(v.x, v.x, ss4.x); ss4.y = fmaf(v.y, v.y, ss4.y); ss4.z = fmaf(v.z, v.z, ss4.z); ss4.w = fmaf(v.w, v.w, ss4.w);
           }
           mbar_wait(&S->op_empty[os_], ophase ^ 1u);
           tc_fence_after_sync();
-          {
-            const uint32_t taddr = trow + (uint32_t)(os_ * 64);
+          const uint32_t taddr = trow + (uint32_t)(os_ * 64);
+          {   // columns 0..15 of the chunk
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int c = 0; c < 4; ++c) split4(x[c], hi + 4 * c, lo + 4 * c);
             tmem_st_32x32b_x16(taddr, hi);
             tmem_st_32x32b_x16(taddr + 32, lo);
-            if (second) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) split4(x[4 + c], hi + 4 * c, lo + 4 * c);
-              tmem_st_32x32b_x16(taddr + 16, hi);
-              tmem_st_32x32b_x16(taddr + 48, lo);
-            }
-            tmem_st_wait();
           }
+          if (second) {   // columns 16..31: second pass over the same registers
+#pragma unroll
+            for (int c = 0; c < 4; ++c) x[c] = *reinterpret_cast<const float4*>(xrow + (((4 + c) ^ sw) << 4));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 v = x[c];
+              ss4.x = fmaf(v.x, v.x, ss4.x); ss4.y = fmaf(v.y, v.y, ss4.y); ss4.z = fmaf(v.z, v.z, ss4.z); ss4.w = fmaf(v.w, v.w, ss4.w);
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) split4(x[c], hi + 4 * c, lo + 4 * c);
+            tmem_st_32x32b_x16(taddr + 16, hi);
+            tmem_st_32x32b_x16(taddr + 48, lo);
+          }
+          tmem_st_wait();
           if (ck == nch - 1) S->ss_d[nr][row] = (ss4.x + ss4.y) + (ss4.z + ss4.w);
           tc_fence_before_sync();
           __syncwarp();
@@ -437,7 +445,6 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
   } else {
     // ------------------------------- epilogue ------------------------------------
-    setmaxnreg_inc<kRegsEpilogue>();
     TKL_WALK();
     if (have_work) {
       const int ew = warp - kFirstEpiWarp;       // 0..15

@@ -62,3 +62,35 @@ def test_gloo_world2_topk_merge_matches_single_process(tmp_path):
         s, i = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))
         assert torch.equal(i, ref_i), f"rank {r}: ids differ"
         assert torch.allclose(s, ref_s, rtol=1e-5, atol=1e-5)
+
+
+def _loop_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from matchmaker_b200 import rerank_loop as RL
+        batches = [{"query_id": [f"q{i % 3}"] * 4, "doc_id": [f"d{i}_{j}" for j in range(4)]} for i in range(7)]
+        local = {}
+        for b in RL.shard_batches(batches, rank, world):
+            for q, d in zip(b["query_id"], b["doc_id"]):
+                local.setdefault(q, []).append((d, float(len(d))))
+        merged = RL.gather_results(local)
+        torch.save(merged, os.path.join(out_dir, f"m{rank}.pt"))
+        m = RL.wrap_data_parallel(torch.nn.Linear(3, 1), torch.device("cpu"))
+        assert type(m).__name__ == "DistributedDataParallel"
+        m(torch.ones(2, 3)).sum().backward()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gloo_world2_rerank_sharding(tmp_path):
+    """shard_batches / gather_results / wrap_data_parallel of the one-process-per-GPU re-ranking path, on gloo."""
+    world, port = 2, _free_port()
+    mp.spawn(_loop_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    merged = [torch.load(os.path.join(str(tmp_path), f"m{r}.pt")) for r in range(world)]
+    assert merged[0].keys() == merged[1].keys() == {"q0", "q1", "q2"}
+    for q in merged[0]:
+        assert sorted(merged[0][q]) == sorted(merged[1][q])
+    assert sum(len(v) for v in merged[0].values()) == 28
