@@ -71,4 +71,9 @@ def test_from_config_reads_the_reference_keys():
     cfg_tkl = dict(cfg, tk_kernels_mu=MU11, tk_kernels_sigma=SG11, max_doc_length=2000)
     assert _layout(get_model_class("TKL").from_config(cfg_tkl, 300)) == LAYOUT["tkl_emb300_k11_len2000_embedding"]
     with pytest.raises(KeyError):
-        get_model_class("conv_knrm")   # outside the hot path: fails loudly instead of silently substituting
+        get_model_class("matchpyramid")   # outside the hot path: fails loudly instead of silently substituting
+    # the kernel-pooling variants of SURVEY 8(f) read the reference's keys too (conv_knrm.py:20-25, cikm20_tk_sparse.py:19-29)
+    ck = get_model_class("conv_knrm").from_config({"conv_knrm_ngrams": 3, "conv_knrm_kernels": 11, "conv_knrm_conv_out_dim": 128}, 300)
+    assert ck.dense.weight.shape == (1, 99) and len(ck.convolutions) == 3
+    ts = get_model_class("TK_Sparse").from_config(dict(cfg, tk_att_proj_dim=32), 300)
+    assert {"mixer_stop", "stop_word_reducer.weight", "stop_word_reducer2.bias", "kernel_alpha_scaler"} <= set(ts.state_dict().keys())
