@@ -69,7 +69,8 @@ constexpr int kReleaseArrivals = 4 + 64;   // lane 0 of each document convert wa
 // The re-deal must fit the registers the CTA was LAUNCHED with (768 threads x 80 = 61 440), not the SM's 64 K: a
 // setmaxnreg.inc beyond that pool never returns.  Only the light warpgroup gives registers back; the others keep 80.
 constexpr int kRegsLight = 56;   // convert and epilogue warps keep the 80 registers of the launch
-constexpr int kCsStride = 44;             // floats per cosine-tile row (11 16-byte units: conflict-free 16-byte row writes)
+constexpr int kCsStride = 122;            // floats per QUERY ROW of the cosine tile cs[i][position]: even (8-byte pair loads), 122 mod 32 = 26
+                                          // puts the 3-4 query rows a warp reads at once on distinct bank pairs
 constexpr int kSatStride = 33;            // table row stride (token counts 0..30)
 constexpr float kSentinel = 1.0e6f;
 constexpr float kTinyNorm = 1e-13f;
@@ -92,7 +93,8 @@ struct TsShared {
   float red[kMaxLq];          // sat_emb_reduce1(q_i)
   float qm[kMaxLq];
   float sp[16];
-  int lenw[64];               // 16 x token count of the window ending at each pair of the tile (byte offset into a sat row)
+  alignas(16) uint16_t lenw[kBlocks][16]; // 16 x token count of the window ending at each pair of the tile (byte offset into a sat row),
+                              // 15 per block in a 32-byte row: two 16-byte loads per block
   float dmring[256];          // unmasked flag of the document's positions, indexed by position & 255
   float part[kEpiWarps][64];  // per-warp partial window scores
   float4 sat[kMaxLq * kSatStride];   // (sat1 * gate, sat2, sat3 * gate, -) per (query row, token count)
@@ -235,8 +237,8 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* qring = smem;                                                    // [kOps][Qhi;Qlo]
   uint8_t* raws = smem + kOps * kQopBytes;                                  // [n_raw][Dx | Qx]
-  float* cs = reinterpret_cast<float*>(raws + (size_t)n_raw * kRawBytes);   // [120][kCsStride] cosine tile
-  TsShared* S = reinterpret_cast<TsShared*>(cs + kTileRows * kCsStride);
+  float* cs = reinterpret_cast<float*>(raws + (size_t)n_raw * kRawBytes);   // [40 query rows][kCsStride] cosine tile
+  TsShared* S = reinterpret_cast<TsShared*>(cs + kMaxLq * kCsStride);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = (P.D + 31) / 32;
@@ -547,9 +549,9 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             for (int j = 0; j < 8; ++j) v[j] = valid ? (__uint_as_float(h8[j]) + __uint_as_float(l8[j])) * rsd * rq[j] : kSentinel;
 #pragma unroll
             for (int j = 0; j < 2; ++j) v[8 + j] = valid ? (__uint_as_float(h2[j]) + __uint_as_float(l2[j])) * rsd * rq[8 + j] : kSentinel;
-            float* dst = cs + row * kCsStride + 10 * cg;
+            float* dst = cs + (10 * cg) * kCsStride + row;   // transposed: consecutive positions of one query row are adjacent
 #pragma unroll
-            for (int j = 0; j < 5; ++j) *reinterpret_cast<float2*>(dst + 2 * j) = make_float2(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 10; ++j) dst[j * kCsStride] = v[j];
             if (cg == 0) S->dmring[(t * kTileRows + row) & 255] = valid ? 1.f : 0.f;
           }
         }
@@ -565,17 +567,18 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             const int pos = last - u;
             if (pos >= 0) n += S->dmring[pos & 255];
           }
-          S->lenw[et] = 16 * (int)n;
+          S->lenw[et / kBlk][et % kBlk] = (uint16_t)(16 * (int)n);
         }
         named_bar_sync(3, kEpiThreads);
         // ---- phase B: activations, block prefix / suffix, windows ------------------------------------------------
         if (ew < n_act_warps) {
           if (tw.halo) {
             // halo tile: only the suffix sums of its last block are wanted
-            const float* cblk = cs + (2 * kBlk * (kBlocks - 1)) * kCsStride + qi;
+            const float2* cblk = reinterpret_cast<const float2*>(cs + qi * kCsStride + 2 * kBlk * (kBlocks - 1));
 #pragma unroll
             for (int r = 0; r < kBlk; ++r) {
-              const float x0 = fmaf(cblk[(2 * r) * kCsStride], a_k, nma_k), x1 = fmaf(cblk[(2 * r + 1) * kCsStride], a_k, nma_k);
+              const float2 c = cblk[r];
+              const float x0 = fmaf(c.x, a_k, nma_k), x1 = fmaf(c.y, a_k, nma_k);
               suf[r] = ex2f(-x0 * x0) + ex2f(-x1 * x1);
             }
 #pragma unroll
@@ -587,16 +590,21 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             for (int j = 0; j < kBlocks; ++j) {
               float tv[16];
               float pre = 0.f;
-              const float* cblk = cs + (2 * kBlk * j) * kCsStride + qi;
-              const int* lw = S->lenw + kBlk * j;
+              const float2* cblk = reinterpret_cast<const float2*>(cs + qi * kCsStride + 2 * kBlk * j);
+              uint32_t lw[8];   // the block's 15 window token counts: two 16-byte loads instead of 15 scalar ones
+              {
+                const uint4 la = *reinterpret_cast<const uint4*>(&S->lenw[j][0]), lb = *reinterpret_cast<const uint4*>(&S->lenw[j][8]);
+                lw[0] = la.x; lw[1] = la.y; lw[2] = la.z; lw[3] = la.w; lw[4] = lb.x; lw[5] = lb.y; lw[6] = lb.z; lw[7] = lb.w;
+              }
 #pragma unroll
               for (int r = 0; r < kBlk; ++r) {
-                const float x0 = fmaf(cblk[(2 * r) * kCsStride], a_k, nma_k), x1 = fmaf(cblk[(2 * r + 1) * kCsStride], a_k, nma_k);
+                const float2 c = cblk[r];
+                const float x0 = fmaf(c.x, a_k, nma_k), x1 = fmaf(c.y, a_k, nma_k);
                 const float u = ex2f(-x0 * x0) + ex2f(-x1 * x1);
                 pre = r == 0 ? u : pre + u;
                 const float Ssum = r < kBlk - 1 ? suf[r + 1] + pre : pre;
                 suf[r] = u;   // suf[r] of the previous block was consumed by window r - 1
-                const int lenb = lw[r];
+                const int lenb = (int)((lw[r >> 1] >> (16 * (r & 1))) & 0xffffu);
                 if (SAT == 0) {
                   const float4 st = *reinterpret_cast<const float4*>(sat_row + lenb);
                   const float pw = ex2f(st.y * lg2f(fmaxf(Ssum, kClamp)));
@@ -673,7 +681,7 @@ int tkl_window_ts_launch(TklParams& P, const DeviceInfo& dev, cudaStream_t strea
   *plan_out = nullptr;
   if (P.Lq > kMaxLq || P.K > 16 || P.Lq * P.K > kEpiThreads || P.D % 4 != 0) return MMB200_OK;
   if (P.B * (int64_t)P.C >= (1ll << 31) || P.B >= (1ll << 31) - 8) return MMB200_OK;
-  const size_t fixed = (size_t)kOps * kQopBytes + (size_t)kTileRows * kCsStride * sizeof(float) + sizeof(TsShared) + 1024;
+  const size_t fixed = (size_t)kOps * kQopBytes + (size_t)kMaxLq * kCsStride * sizeof(float) + sizeof(TsShared) + 1024;
   const int n_raw = std::min<int>(kMaxRaw, (int)(((size_t)dev.max_smem_optin - fixed) / kRawBytes));
   if (n_raw < 2) return MMB200_OK;
   const size_t smem = fixed + (size_t)n_raw * kRawBytes;
