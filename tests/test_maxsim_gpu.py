@@ -176,6 +176,42 @@ def test_ragged_fetch_is_bit_identical():
         assert torch.equal(nomask, interaction.maxsim(args[0], args[1], docs_per_query=dpq, impl="tcgen05"))
 
 
+def test_argmax_from_the_tcgen05_epilogue_matches_the_simt_kernel():
+    """Training-mode forward: the queries-on-M kernel tracks the winning document row per query token itself (autograd
+    no longer drops to the SIMT kernel).  Scores bit-identical to the inference instantiation; argmax = the first maximum
+    of the fp32 scores; -1 for masked query tokens, fully masked documents and maxima taken by the -1000 fill."""
+    for (n_q, dpq, Lq, Ld, dim) in [(6, 50, 32, 180, 128), (3, 4, 17, 300, 64), (2, 5, 32, 77, 128)]:
+        q, d, qm, dm = O.synth_colbert_inputs(n_q, dpq, Lq, Ld, dim, seed=90 + Ld, full_q=False)
+        dm[1] = 0                      # fully masked document: no gradient anywhere
+        dm[2, :] = 1
+        # document 3: every row = -2000 x (sum of its query's tokens), so most real scores fall below the -1000 fill of its
+        # masked half and the fill wins those maxima (no gradient there)
+        d[3, :, :] = (-2000.0 * q[3 // dpq].float().sum(0)).to(d.dtype)
+        dm[3, Ld // 2:] = 0
+        args = _cuda(q, d, qm, dm)
+        s_inf = interaction.maxsim(*args, docs_per_query=dpq, impl="tcgen05")
+        s_trn, am = interaction.maxsim(*args, docs_per_query=dpq, impl="tcgen05", return_argmax=True)
+        assert torch.equal(s_inf, s_trn)
+        s_simt, am_simt = interaction.maxsim(*args, docs_per_query=dpq, impl="simt", return_argmax=True)
+        # the oracle's own argmax (fp32 bmm on the upcast values), first maximum
+        qe = q.float().repeat_interleave(dpq, dim=0)
+        sc = torch.bmm(qe, d.float().transpose(1, 2))
+        sc = sc.masked_fill(~dm.bool().unsqueeze(1), -1000.0)
+        ref_max, ref_arg = sc.max(-1)
+        ref_arg = ref_arg.masked_fill(~dm.bool().gather(1, ref_arg), -1)              # the fill won (or everything masked)
+        ref_arg = ref_arg.masked_fill(~qm.bool().repeat_interleave(dpq, dim=0), -1)   # masked query token
+        am, am_simt = am.cpu().long(), am_simt.cpu().long()
+        # where the two largest scores of a row are separated beyond fp32 round-off the winner is unambiguous
+        top2 = sc.topk(2, dim=-1).values
+        clear = (top2[..., 0] - top2[..., 1]) > 1e-4 * top2[..., 0].abs().clamp(min=1.0)
+        assert (am[clear] == ref_arg[clear]).all()
+        assert (am_simt[clear] == ref_arg[clear]).all()
+        assert (am[ref_arg < 0] == -1).all()
+        # ragged fetch + argmax
+        s_rag, am_rag = interaction.maxsim(*args, docs_per_query=dpq, impl="tcgen05_ragged", return_argmax=True)
+        assert torch.equal(s_rag, s_inf) and torch.equal(am_rag.cpu().long(), am)
+
+
 def test_host_buffer_pipeline_matches_device_path():
     q, d, qm, dm = O.synth_colbert_inputs(4, 250, 32, 180, 128, seed=21)
     ref = interaction.maxsim(*_cuda(q, d, qm, dm), docs_per_query=250)
