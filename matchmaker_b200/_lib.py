@@ -10,7 +10,9 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmatchmaker_b200.so")
+# MMB200_LIB: load another build of the SAME library (A/B measurements of two kernel versions on one box); the default is
+# the in-tree build.  Either way a missing file raises -- there is no fallback implementation behind it.
+LIB_PATH = os.environ.get("MMB200_LIB") or os.path.join(_HERE, "csrc", "libmatchmaker_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3

@@ -169,9 +169,21 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       uint32_t phase = 0;
       int64_t prev_q = -1;
       uint32_t qcount = 0;
+      // ragged fetch: the row counts of the next documents are loaded four pairs ahead -- a load issued when its value is
+      // needed would put one global-memory latency (~0.8 us) into every document of a kernel that wants ~0.5 us each
+      int nr_ring[4] = {0, 0, 0, 0};
+      if (P.rows_needed)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          if (p_begin + a < p_end) nr_ring[a] = P.rows_needed[p_begin + a];
       for (int64_t p = p_begin; p < p_end; ++p) {
         const int64_t qi = P.pair_q ? (int64_t)P.pair_q[p] : (p + P.pair_base) / P.docs_per_query;
         const int64_t di = P.pair_d ? (int64_t)P.pair_d[p] : p;
+        const int need_packed = nr_ring[0];
+        if (P.rows_needed) {
+          nr_ring[0] = nr_ring[1]; nr_ring[1] = nr_ring[2]; nr_ring[2] = nr_ring[3];
+          nr_ring[3] = p + 4 < p_end ? P.rows_needed[p + 4] : 0;
+        }
         if (qi != prev_q) {
           const uint32_t slot = qcount & 1u, use = qcount >> 1;
           mbar_wait(&S->qempty[slot], (use & 1u) ^ 1u);
@@ -183,7 +195,7 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           ++qcount;
           prev_q = qi;
         }
-        const int need_rows = P.rows_needed ? (P.rows_needed[di] & kRowsMask) : 0;
+        const int need_rows = need_packed & kRowsMask;
         for (int t = 0; t < L.tiles; ++t) {
           mbar_wait(&S->empty[stage], phase ^ 1u);
           uint8_t* dst = stage_base + (size_t)stage * L.stage_bytes;
@@ -222,7 +234,11 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (lane == 0) {
       const uint32_t idesc_full = make_idesc((uint32_t)L.fmt, 128, (uint32_t)L.tn);
       const uint64_t ones_desc = make_noswz_k16_desc(smem_u32(ones_tile));
-      int need_next = P.rows_needed && p_begin < p_end ? (P.rows_needed[P.pair_d ? P.pair_d[p_begin] : p_begin] & kRowsMask) : 0;
+      int nr_ring[4] = {0, 0, 0, 0};   // row counts four pairs ahead (see the TMA producer)
+      if (P.rows_needed)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          if (p_begin + a < p_end) nr_ring[a] = P.rows_needed[p_begin + a] & kRowsMask;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -240,8 +256,11 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           prev_q = qi;
         }
         const uint32_t qaddr = smem_u32(q_base + (size_t)cur_slot * qslot_bytes);
-        const int need = need_next;
-        if (P.rows_needed && p + 1 < p_end) need_next = P.rows_needed[P.pair_d ? P.pair_d[p + 1] : p + 1] & kRowsMask;
+        const int need = nr_ring[0];
+        if (P.rows_needed) {
+          nr_ring[0] = nr_ring[1]; nr_ring[1] = nr_ring[2]; nr_ring[2] = nr_ring[3];
+          nr_ring[3] = p + 4 < p_end ? (P.rows_needed[p + 4] & kRowsMask) : 0;
+        }
         for (int t = 0; t < L.tiles; ++t) {
           // ragged fetch: multiply only the columns that hold fetched rows
           const uint32_t idesc = P.rows_needed ? make_idesc((uint32_t)L.fmt, 128, (uint32_t)ragged_cols(need, t, L.tn)) : idesc_full;
@@ -270,7 +289,10 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int dmt = P.d_mask ? P.mask_dtype : MMB200_MASK_NONE;
     int stage = 0;
     uint32_t phase = 0;
-    uint64_t raw[8], raw_next[8];
+    // mask words are fetched kAhead tiles before they are needed: one tile ahead hides a global-memory latency only while
+    // a document takes ~1 us (dense fetch at HBM speed); the ragged fetch wants ~0.5 us per document
+    constexpr int kAhead = 3;
+    uint64_t raw[8], ring[kAhead][8];
     auto fetch = [&](int64_t p, int t, uint64_t (&dst)[8]) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -280,18 +302,24 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           dst[k] = mask_raw(P.d_mask, dmt, pair_dmask_row_of(P, p) * (int64_t)P.Ld + g);
       }
     };
-    fetch(p_begin, 0, raw_next);
+    int64_t fp = p_begin;   // (pair, tile) the next fetch is for
+    int ft = 0;
+    auto advance = [&]() {
+      if (++ft == L.tiles) { ft = 0; ++fp; }
+    };
+#pragma unroll
+    for (int a = 0; a < kAhead; ++a) { fetch(fp, ft, ring[a]); advance(); }
     for (int64_t p = p_begin; p < p_end; ++p) {
       bool any_masked = false;
       for (int t = 0; t < L.tiles; ++t) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) raw[k] = raw_next[k];
-        {  // prefetch the mask words of the next tile
-          int nt = t + 1;
-          int64_t np = p;
-          if (nt == L.tiles) { nt = 0; ++np; }
-          fetch(np, nt, raw_next);
-        }
+        for (int k = 0; k < 8; ++k) raw[k] = ring[0][k];
+#pragma unroll
+        for (int a = 0; a + 1 < kAhead; ++a)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) ring[a][k] = ring[a + 1][k];
+        fetch(fp, ft, ring[kAhead - 1]);
+        advance();
         uint16_t pen[8];
         bool masked_here = false;
 #pragma unroll
@@ -331,7 +359,7 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (lane < P.Lq) qraw = (qmt != MMB200_MASK_NONE) ? mask_raw(P.q_mask, qmt, qi * (int64_t)P.Lq + lane) : 1;
       float m = -INFINITY;
       int am = -1;   // row of the running maximum (first one on ties); stays -1 when nothing beats -inf
-      const int packed_rows = P.rows_needed ? P.rows_needed[P.pair_d ? P.pair_d[p] : p] : 0;
+      const int packed_rows = P.rows_needed ? P.rows_needed[p] : 0;   // ragged fetch implies pair_d == nullptr (launcher)
       for (int t = 0; t < L.tiles; ++t) {
         const int ncols = P.rows_needed ? ragged_cols(packed_rows & kRowsMask, t, L.tn) : L.tn;
         const int n32 = ncols >> 5;
@@ -390,7 +418,10 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (lane == 0) mbar_arrive(&S->accempty[acc]);
       }
       // ragged fetch: the reference's -1000 fill (any masked position below Ld) joins the max here
-      if (P.rows_needed && (packed_rows & kAnyMaskedBit)) m = fmaxf(m, -1000.0f);
+      if (P.rows_needed && (packed_rows & kAnyMaskedBit) && -1000.0f > m) {
+        m = -1000.0f;
+        am = -1;   // the fill won: no gradient (the dense fetch reports its virtual row, >= Ld, to the same effect)
+      }
       if constexpr (kArgmax) {
         // rows >= Ld are the -inf padding and the virtual -1000 row: a max taken there carries no gradient (-1), like a
         // masked query token
