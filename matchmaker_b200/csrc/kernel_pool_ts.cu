@@ -376,7 +376,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const uint32_t live = __ballot_sync(0xffffffffu, valid);
             if (lane == 0) S->live[tile_seq & 1][qd] = live ? qd * 32 + 32 - __clz(live) : 0;
             // gate g_j * exp(-x^2) = 2^(-u^2 + log2 g_j): one exponent term per document row, no extra multiply
-            if (P.gate) S->lg[tile_seq & 1][row] = g < P.Ld ? __log2f(fmaxf(P.gate[p * (int64_t)P.Ld + g], 0.f)) : 0.f;
+            S->lg[tile_seq & 1][row] = (P.gate && g < P.Ld) ? __log2f(fmaxf(P.gate[p * (int64_t)P.Ld + g], 0.f)) : 0.f;
           }
           tc_fence_before_sync();
           __syncwarp();
@@ -400,33 +400,20 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           auto cos_at = [&](int r) -> float {
             return r < rows_live ? cbuf[r * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)] : kSentinel;
           };
+          const float* lgs = S->lg[tile_seq & 1];
           float c0 = cos_at(ew), c1 = cos_at(ew + 8);
-          if (P.gate == nullptr) {   // warp-uniform: the ungated loop carries no gate loads (the phase is MUFU / MIO-bound)
-            for (int r = ew; r < rows_live; r += 16) {
-              const float n0 = cos_at(r + 16), n1 = cos_at(r + 24);
+          float l0 = lgs[ew], l1 = lgs[ew + 8];
+          for (int r = ew; r < rows_live; r += 16) {
+            const float n0 = cos_at(r + 16), n1 = cos_at(r + 24);
+            const float m0 = lgs[(r + 16) & 127], m1 = lgs[(r + 24) & 127];
 #pragma unroll
-              for (int k = 0; k < KB; ++k) {
-                const float m = kRegConst ? mu_r[k] : S->mu[k], a = kRegConst ? a_r[k] : S->a[k];
-                const float u0 = (c0 - m) * a, u1 = (c1 - m) * a;
-                acc[k] += ex2f(-u0 * u0) + ex2f(-u1 * u1);
-              }
-              c0 = n0; c1 = n1;
+            for (int k = 0; k < KB; ++k) {
+              const float m = kRegConst ? mu_r[k] : S->mu[k], a = kRegConst ? a_r[k] : S->a[k];
+              const float u0 = (c0 - m) * a, u1 = (c1 - m) * a;
+              acc[k] += ex2f(fmaf(-u0, u0, l0)) + ex2f(fmaf(-u1, u1, l1));
             }
-          } else {
-            const float* lgs = S->lg[tile_seq & 1];
-            float l0 = lgs[ew], l1 = lgs[ew + 8];
-            for (int r = ew; r < rows_live; r += 16) {
-              const float n0 = cos_at(r + 16), n1 = cos_at(r + 24);
-              const float m0 = lgs[(r + 16) & 127], m1 = lgs[(r + 24) & 127];
-#pragma unroll
-              for (int k = 0; k < KB; ++k) {
-                const float m = kRegConst ? mu_r[k] : S->mu[k], a = kRegConst ? a_r[k] : S->a[k];
-                const float u0 = (c0 - m) * a, u1 = (c1 - m) * a;
-                acc[k] += ex2f(fmaf(-u0, u0, l0)) + ex2f(fmaf(-u1, u1, l1));
-              }
-              c0 = n0; c1 = n1;
-              l0 = m0; l1 = m1;
-            }
+            c0 = n0; c1 = n1;
+            l0 = m0; l1 = m1;
           }
         }
         if (PROF) pc[2] += clock64() - t_b;

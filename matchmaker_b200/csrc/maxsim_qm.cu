@@ -83,16 +83,6 @@ __device__ __forceinline__ uint32_t penalty_offset(int row) { return (uint32_t)(
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-// rows_needed[di] (ragged fetch) packs two facts about document di: bits 0..29 = 1 + index of its last unmasked row,
-// bit 30 = some position below Ld is masked (then the reference's -1000 fill takes part in every max, colbert.py:69).
-constexpr int kRowsMask = 0x3fffffff, kAnyMaskedBit = 1 << 30;
-// MMA N / accumulator columns used for tile t of a document with `need` rows worth fetching: the rows rounded up to 16
-// (UMMA N granularity), at least 16, at most the tile
-__device__ __forceinline__ int ragged_cols(int need, int t, int tn) {
-  const int rows = min(max(need - t * tn, 0), tn);
-  return max(16, (rows + 15) & ~15);
-}
-
 __device__ __forceinline__ int64_t pair_dmask_row_of(const MaxsimParams& P, int64_t p) {
   if (P.pair_dmask) return (int64_t)P.pair_dmask[p];
   return P.pair_d ? (int64_t)P.pair_d[p] : p;
@@ -104,9 +94,7 @@ __device__ __forceinline__ int64_t pair_dmask_row_of(const MaxsimParams& P, int6
 template <bool kArgmax>
 __global__ void __launch_bounds__(kThreads, 1)
 maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
-                 const __grid_constant__ CUtensorMap tmap_d16, const __grid_constant__ CUtensorMap tmap_d32,
-                 const __grid_constant__ CUtensorMap tmap_d64, const __grid_constant__ CUtensorMap tmap_d128, MaxsimParams P,
-                 QmLaunch L) {
+                 const __grid_constant__ CUtensorMap tmap_d16, MaxsimParams P, QmLaunch L) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment for SWIZZLE_128B tiles, derived by pointer arithmetic on the __shared__ array so the
   // compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
@@ -169,21 +157,9 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       uint32_t phase = 0;
       int64_t prev_q = -1;
       uint32_t qcount = 0;
-      // ragged fetch: the row counts of the next documents are loaded four pairs ahead -- a load issued when its value is
-      // needed would put one global-memory latency (~0.8 us) into every document of a kernel that wants ~0.5 us each
-      int nr_ring[4] = {0, 0, 0, 0};
-      if (P.rows_needed)
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          if (p_begin + a < p_end) nr_ring[a] = P.rows_needed[p_begin + a];
       for (int64_t p = p_begin; p < p_end; ++p) {
         const int64_t qi = P.pair_q ? (int64_t)P.pair_q[p] : (p + P.pair_base) / P.docs_per_query;
         const int64_t di = P.pair_d ? (int64_t)P.pair_d[p] : p;
-        const int need_packed = nr_ring[0];
-        if (P.rows_needed) {
-          nr_ring[0] = nr_ring[1]; nr_ring[1] = nr_ring[2]; nr_ring[2] = nr_ring[3];
-          nr_ring[3] = p + 4 < p_end ? P.rows_needed[p + 4] : 0;
-        }
         if (qi != prev_q) {
           const uint32_t slot = qcount & 1u, use = qcount >> 1;
           mbar_wait(&S->qempty[slot], (use & 1u) ^ 1u);
@@ -195,7 +171,7 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           ++qcount;
           prev_q = qi;
         }
-        const int need_rows = need_packed & kRowsMask;
+        const int need_rows = P.rows_needed ? P.rows_needed[di] : 0;
         for (int t = 0; t < L.tiles; ++t) {
           mbar_wait(&S->empty[stage], phase ^ 1u);
           uint8_t* dst = stage_base + (size_t)stage * L.stage_bytes;
@@ -203,26 +179,18 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             mbar_arrive_expect_tx(&S->full[stage], (uint32_t)L.doc_bytes);
             tma_load_4d(&tmap_d, dst, &S->full[stage], 0, t * L.tn, 0, (int)di, kEvictFirst);
           } else {
-            // rows up to the document's last unmasked one, rounded up to 16, as the fewest boxes of 128 / 64 / 32 / 16 rows
-            // (a 75-token document: 64 + 16 rows = 2 boxes per k-block instead of five 16-row ones); the rest of the stage
-            // keeps stale (finite) rows that neither the MMA (N = ragged_cols) nor the epilogue looks at
+            // 16-row blocks up to the document's last unmasked row; the rest of the stage keeps stale
+            // (finite) rows, which the penalty tile masks with -inf
             const int rows_here = min(max(need_rows - t * L.tn, 0), L.tn);
             const int nb = (rows_here + 15) >> 4;
             if (nb == 0) {
               mbar_arrive(&S->full[stage]);
             } else {
               mbar_arrive_expect_tx(&S->full[stage], (uint32_t)(nb * L.kblocks * 2048));
-              for (int kb = 0; kb < L.kblocks; ++kb) {
-                int b16 = 0;
-                while (b16 < nb) {
-                  const int left = nb - b16;
-                  const CUtensorMap* m = left >= 8 ? &tmap_d128 : left >= 4 ? &tmap_d64 : left >= 2 ? &tmap_d32 : &tmap_d16;
-                  const int step = left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
-                  tma_load_4d(m, dst + kb * L.tn * 128 + b16 * 2048, &S->full[stage], 0, t * L.tn + b16 * 16, kb, (int)di,
-                              kEvictFirst);
-                  b16 += step;
-                }
-              }
+              for (int kb = 0; kb < L.kblocks; ++kb)
+                for (int b16 = 0; b16 < nb; ++b16)
+                  tma_load_4d(&tmap_d16, dst + kb * L.tn * 128 + b16 * 2048, &S->full[stage], 0, t * L.tn + b16 * 16, kb,
+                              (int)di, kEvictFirst);
             }
           }
           if (++stage == L.stages) { stage = 0; phase ^= 1u; }
@@ -232,13 +200,8 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   } else if (warp == 3) {
     // ------------------------------- MMA issuer ---------------------------------
     if (lane == 0) {
-      const uint32_t idesc_full = make_idesc((uint32_t)L.fmt, 128, (uint32_t)L.tn);
+      const uint32_t idesc = make_idesc((uint32_t)L.fmt, 128, (uint32_t)L.tn);
       const uint64_t ones_desc = make_noswz_k16_desc(smem_u32(ones_tile));
-      int nr_ring[4] = {0, 0, 0, 0};   // row counts four pairs ahead (see the TMA producer)
-      if (P.rows_needed)
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          if (p_begin + a < p_end) nr_ring[a] = P.rows_needed[p_begin + a] & kRowsMask;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -256,14 +219,7 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           prev_q = qi;
         }
         const uint32_t qaddr = smem_u32(q_base + (size_t)cur_slot * qslot_bytes);
-        const int need = nr_ring[0];
-        if (P.rows_needed) {
-          nr_ring[0] = nr_ring[1]; nr_ring[1] = nr_ring[2]; nr_ring[2] = nr_ring[3];
-          nr_ring[3] = p + 4 < p_end ? (P.rows_needed[p + 4] & kRowsMask) : 0;
-        }
         for (int t = 0; t < L.tiles; ++t) {
-          // ragged fetch: multiply only the columns that hold fetched rows
-          const uint32_t idesc = P.rows_needed ? make_idesc((uint32_t)L.fmt, 128, (uint32_t)ragged_cols(need, t, L.tn)) : idesc_full;
           mbar_wait(&S->accempty[acc], accphase ^ 1u);
           mbar_wait(&S->full[stage], phase);
           tc_fence_after_sync();
@@ -289,10 +245,7 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int dmt = P.d_mask ? P.mask_dtype : MMB200_MASK_NONE;
     int stage = 0;
     uint32_t phase = 0;
-    // mask words are fetched kAhead tiles before they are needed: one tile ahead hides a global-memory latency only while
-    // a document takes ~1 us (dense fetch at HBM speed); the ragged fetch wants ~0.5 us per document
-    constexpr int kAhead = 3;
-    uint64_t raw[8], ring[kAhead][8];
+    uint64_t raw[8], raw_next[8];
     auto fetch = [&](int64_t p, int t, uint64_t (&dst)[8]) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -302,24 +255,18 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           dst[k] = mask_raw(P.d_mask, dmt, pair_dmask_row_of(P, p) * (int64_t)P.Ld + g);
       }
     };
-    int64_t fp = p_begin;   // (pair, tile) the next fetch is for
-    int ft = 0;
-    auto advance = [&]() {
-      if (++ft == L.tiles) { ft = 0; ++fp; }
-    };
-#pragma unroll
-    for (int a = 0; a < kAhead; ++a) { fetch(fp, ft, ring[a]); advance(); }
+    fetch(p_begin, 0, raw_next);
     for (int64_t p = p_begin; p < p_end; ++p) {
       bool any_masked = false;
       for (int t = 0; t < L.tiles; ++t) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) raw[k] = ring[0][k];
-#pragma unroll
-        for (int a = 0; a + 1 < kAhead; ++a)
-#pragma unroll
-          for (int k = 0; k < 8; ++k) ring[a][k] = ring[a + 1][k];
-        fetch(fp, ft, ring[kAhead - 1]);
-        advance();
+        for (int k = 0; k < 8; ++k) raw[k] = raw_next[k];
+        {  // prefetch the mask words of the next tile
+          int nt = t + 1;
+          int64_t np = p;
+          if (nt == L.tiles) { nt = 0; ++np; }
+          fetch(np, nt, raw_next);
+        }
         uint16_t pen[8];
         bool masked_here = false;
 #pragma unroll
@@ -337,9 +284,7 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int k = 0; k < 8; ++k) {
           const int r = lane + 32 * k, g = t * L.tn + r;
           if (r < L.tn) {
-            // dense fetch: the last row of the last tile is the virtual row that carries the -1000 fill; ragged fetch: the
-            // epilogue applies the fill itself (the MMA no longer covers that row)
-            const uint16_t v = (!P.rows_needed && g == L.tiles * L.tn - 1) ? (any_masked ? L.neg_1000 : L.neg_inf) : pen[k];
+            const uint16_t v = (g == L.tiles * L.tn - 1) ? (any_masked ? L.neg_1000 : L.neg_inf) : pen[k];
             *reinterpret_cast<uint16_t*>(pt + penalty_offset(r)) = v;
           }
         }
@@ -352,6 +297,7 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   } else if (warp < 2) {
     // ------------------------------- epilogue ------------------------------------
     const int qmt = P.q_mask ? P.mask_dtype : MMB200_MASK_NONE;
+    const int n32 = L.tn >> 5, tail16 = (L.tn & 16) != 0;
     for (int64_t n = warp; p_begin + n < p_end; n += 2) {
       const int64_t p = p_begin + n;
       const int64_t qi = P.pair_q ? (int64_t)P.pair_q[p] : (p + P.pair_base) / P.docs_per_query;
@@ -359,11 +305,7 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (lane < P.Lq) qraw = (qmt != MMB200_MASK_NONE) ? mask_raw(P.q_mask, qmt, qi * (int64_t)P.Lq + lane) : 1;
       float m = -INFINITY;
       int am = -1;   // row of the running maximum (first one on ties); stays -1 when nothing beats -inf
-      const int packed_rows = P.rows_needed ? P.rows_needed[p] : 0;   // ragged fetch implies pair_d == nullptr (launcher)
       for (int t = 0; t < L.tiles; ++t) {
-        const int ncols = P.rows_needed ? ragged_cols(packed_rows & kRowsMask, t, L.tn) : L.tn;
-        const int n32 = ncols >> 5;
-        const bool tail16 = (ncols & 16) != 0;
         const int64_t u = n * L.tiles + t;  // tile sequence number inside this CTA
         const int acc = (int)(u % L.acc_slots);
         const uint32_t accphase = (uint32_t)((u / L.acc_slots) & 1);
@@ -417,11 +359,6 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&S->accempty[acc]);
       }
-      // ragged fetch: the reference's -1000 fill (any masked position below Ld) joins the max here
-      if (P.rows_needed && (packed_rows & kAnyMaskedBit) && -1000.0f > m) {
-        m = -1000.0f;
-        am = -1;   // the fill won: no gradient (the dense fetch reports its virtual row, >= Ld, to the same effect)
-      }
       if constexpr (kArgmax) {
         // rows >= Ld are the -inf padding and the virtual -1000 row: a max taken there carries no gradient (-1), like a
         // masked query token
@@ -444,23 +381,20 @@ maxsim_qm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
 }  // namespace
 
-// rows_needed[di] = (1 + last unmasked row) | (any masked position ? bit 30 : 0)   (one warp per document)
+// rows_needed[di] = 1 + last unmasked row (one warp per document)
 __global__ void __launch_bounds__(256) rows_needed_kernel(const void* __restrict__ d_mask, int mask_dtype,
                                                           int32_t* __restrict__ rows_needed, int64_t n_d, int Ld) {
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (w >= n_d) return;
-  int last = 0, live = 0;
-  if (!d_mask) { last = Ld; live = lane == 0 ? Ld : 0; }
+  int last = 0;
+  if (!d_mask) last = Ld;
   else
     for (int j = lane; j < Ld; j += 32)
-      if (mask_at(d_mask, mask_dtype, w * Ld + j)) { last = j + 1; ++live; }
+      if (mask_at(d_mask, mask_dtype, w * Ld + j)) last = j + 1;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-    live += __shfl_xor_sync(0xffffffffu, live, o);
-  }
-  if (lane == 0) rows_needed[w] = last | (live < Ld ? kAnyMaskedBit : 0);
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  if (lane == 0) rows_needed[w] = last;
 }
 
 int maxsim_rows_needed_launch(const void* d_mask, int mask_dtype, int32_t* rows_needed, int64_t n_d, int Ld,
@@ -514,12 +448,12 @@ int maxsim_qm_launch(const MaxsimParams& P, int dtype, const DeviceInfo& dev, cu
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
       return rc;
   }
-  CUtensorMap tdr[4];   // ragged fetch: one k-block, 16 / 32 / 64 / 128 rows
-  for (int i = 0; i < 4; ++i) {
+  CUtensorMap td16;
+  {
     const uint64_t dims[4] = {64, (uint64_t)P.Ld, (uint64_t)L.kblocks, (uint64_t)P.n_d};
     const uint64_t strides[3] = {(uint64_t)P.dim * 2, 128, (uint64_t)P.Ld * P.dim * 2};
-    const uint32_t box[4] = {64, (uint32_t)(16 << i), 1, 1};
-    if (int rc = encode_tensor_map(&tdr[i], tdt, 4, P.d, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+    const uint32_t box[4] = {64, 16, 1, 1};
+    if (int rc = encode_tensor_map(&td16, tdt, 4, P.d, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
       return rc;
   }
@@ -527,10 +461,10 @@ int maxsim_qm_launch(const MaxsimParams& P, int dtype, const DeviceInfo& dev, cu
   const int grid = (int)std::min<int64_t>(dev.sm_count, P.n_pairs);
   if (P.argmax) {
     MMB_CHECK_CUDA(cudaFuncSetAttribute(maxsim_qm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    maxsim_qm_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(tq, td, tdr[0], tdr[1], tdr[2], tdr[3], P, L);
+    maxsim_qm_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(tq, td, td16, P, L);
   } else {
     MMB_CHECK_CUDA(cudaFuncSetAttribute(maxsim_qm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    maxsim_qm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tq, td, tdr[0], tdr[1], tdr[2], tdr[3], P, L);
+    maxsim_qm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tq, td, td16, P, L);
   }
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;

@@ -47,12 +47,33 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 
-// try_wait with a suspend-time hint: a warp whose phase has not completed is parked by the hardware (up to the hint)
-// instead of returning at once, so a role that waits for a slower one does not burn the SM's issue slots on a
-// try_wait / branch loop (ncu on tkl_ts_kernel: the convert warps, waiting on the epilogue-bound pipeline, executed
-// 30 % of all warp instructions before this hint was added).
-constexpr uint32_t kMbarSuspendHintNs = 50000u;  // 50 us: upper bound of one nap, the wait ends when the phase completes
+// Two flavours of the blocking wait, selected per kernel (template argument of mbar_wait):
+//   * polling (default): try_wait returns at once when the phase is still open; the loop re-issues it and checks a clock
+//     watchdog.  Lowest wake-up latency -- right for pipelines whose stages hand over every few hundred cycles and whose
+//     waiting roles have issue slots to spare (max-sim, kernel pooling, flat-IP: same-box A/B, profiles/r02_ab_*.log).
+//   * napping (kNap = true): try_wait carries a suspend-time hint, the hardware parks the warp (ptxas: NANOSLEEP.SYNCS)
+//     until the phase completes or something wakes it, and the watchdog counts wake-ups (3 instructions per turn instead
+//     of 6).  Right when the waiting roles share their schedulers with an issue-bound role: in tkl_ts_kernel the convert
+//     warps, waiting on the epilogue-bound pipeline, executed 30 % of all warp instructions as polling loops.
+// Either way a protocol bug ends in a trap (the launch fails with an error the host reports) instead of a hung GPU.
+#ifndef MMB_WATCHDOG_CYCLES
+#define MMB_WATCHDOG_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz
+#endif
+constexpr uint32_t kMbarSuspendHintNs = 50000u;  // 50 us: upper bound of one nap
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+__device__ __forceinline__ bool mbar_try_wait_nap(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -64,18 +85,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Blocking wait.  Every try_wait parks the warp (suspend hint above) until the phase completes or something wakes it;
-// the watchdog counts wake-ups instead of reading the clock (3 instructions per turn instead of 6: roles that wait on
-// a slower role share their scheduler with it): 2^18 futile wake-ups (13 s of naps in a true deadlock, milliseconds of back-to-back wake-ups; no protocol here
-// waits that long) end in a trap, so a protocol bug fails the launch instead of hanging the GPU.
+template <bool kNap = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 18)) {
-      printf("mmb200: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
+  if constexpr (kNap) {
+    if (mbar_try_wait_nap(bar, parity)) return;
+    uint32_t spins = 0;   // 2^18 futile wake-ups: 13 s of naps in a true deadlock, milliseconds of back-to-back wake-ups
+    while (!mbar_try_wait_nap(bar, parity)) {
+      if (++spins > (1u << 18)) {
+        printf("mmb200: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+               smem_u32(bar), parity);
+        __trap();
+      }
+    }
+  } else {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+      if (clock64() - t0 > MMB_WATCHDOG_CYCLES) {
+        printf("mmb200: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+               smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }

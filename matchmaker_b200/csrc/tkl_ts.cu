@@ -280,7 +280,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         const uint32_t bytes = (uint32_t)(n_present * kSlotBytes + kQxBytes);
         for (int ck = 0; ck < nch; ++ck) {
-          mbar_wait(&S->raw_empty[stage], phase ^ 1u);
+          mbar_wait<true>(&S->raw_empty[stage], phase ^ 1u);
           uint8_t* st = raws + (size_t)stage * kRawBytes;
           mbar_arrive_expect_tx(&S->raw_full[stage], bytes);
 #pragma unroll
@@ -300,12 +300,12 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       int stage = 0, acc = 0;
       uint32_t phase = 0, accphase = 0;
       for (; tw.valid(); tw.next()) {
-        mbar_wait(&S->accempty[acc], accphase ^ 1u);
+        mbar_wait<true>(&S->accempty[acc], accphase ^ 1u);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + (uint32_t)(kAccCol0 + acc * kNq);
         for (int ck = 0; ck < nch; ++ck) {
           const int ksteps = (min(32, P.D - ck * 32) + 7) >> 3;
-          mbar_wait(&S->op_full[stage], phase);
+          mbar_wait<true>(&S->op_full[stage], phase);
           tc_fence_after_sync();
           const uint32_t abase = tmem_base + (uint32_t)(stage * 64);
           const uint64_t b0 = make_sw128_kmajor_desc(smem_u32(qring + (size_t)stage * kQopBytes));
@@ -341,7 +341,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       for (; tw.valid(); tw.next()) {
         float ss[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         for (int ck = 0; ck < nch; ++ck) {
-          mbar_wait(&S->raw_full[rs_], rphase);
+          mbar_wait<true>(&S->raw_full[rs_], rphase);
           const uint8_t* xq = raws + (size_t)rs_ * kRawBytes + kDxBytes;
           float4 x[5];
 #pragma unroll
@@ -350,7 +350,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             x[j] = *reinterpret_cast<const float4*>(xq + row * 128 + ((c ^ (row & 7)) << 4));
             ss[j] = fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, fmaf(x[j].z, x[j].z, fmaf(x[j].w, x[j].w, ss[j]))));
           }
-          mbar_wait(&S->op_empty[os_], ophase ^ 1u);
+          mbar_wait<true>(&S->op_empty[os_], ophase ^ 1u);
           uint8_t* qo = qring + (size_t)os_ * kQopBytes;
 #pragma unroll
           for (int j = 0; j < 5; ++j) {
@@ -397,7 +397,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         float4 ss4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int ck = 0; ck < nch; ++ck) {
           const bool second = P.D - ck * 32 > 16;   // columns 16..31 of this chunk hold data (warp-uniform)
-          mbar_wait(&S->raw_full[rs_], rphase);
+          mbar_wait<true>(&S->raw_full[rs_], rphase);
           const uint8_t* xrow = raws + (size_t)rs_ * kRawBytes + row * 128;
           float4 x[4];
 #pragma unroll
@@ -407,7 +407,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             const float4 v = x[c];
             ss4.x = fmaf(v.x, v.x, ss4.x); ss4.y = fmaf(v.y, v.y, ss4.y); ss4.z = fmaf(v.z, v.z, ss4.z); ss4.w = fmaf(v.w, v.w, ss4.w);
           }
-          mbar_wait(&S->op_empty[os_], ophase ^ 1u);
+          mbar_wait<true>(&S->op_empty[os_], ophase ^ 1u);
           tc_fence_after_sync();
           const uint32_t taddr = trow + (uint32_t)(os_ * 64);
           {   // columns 0..15 of the chunk
@@ -527,7 +527,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           present = pk >= 0;
           if (present) draw = dmt != MMB200_MASK_NONE ? mask_raw(P.chunk_mask, dmt, (int64_t)pk * kChunk + (row % kChunk)) : 1;
         }
-        mbar_wait(&S->accfull[acc_slot], accphase);
+        mbar_wait<true>(&S->accfull[acc_slot], accphase);
         tc_fence_after_sync();
         {
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(kAccCol0 + acc_slot * kNq + 10 * cg);
