@@ -457,7 +457,6 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const int dmt = P.chunk_mask ? P.mask_dtype : MMB200_MASK_NONE;
       const int qmt = P.q_mask ? P.mask_dtype : MMB200_MASK_NONE;
       const int n_ik = P.Lq * P.K;
-      const int n_act_warps = (n_ik + 31) >> 5;
       const bool ik_live = et < n_ik;
       const int qi = ik_live ? et / P.K : 0;     // query row of this thread in phase B
       const int kk = ik_live ? et - qi * P.K : 0;
@@ -471,6 +470,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       int acc_slot = 0, nr = 0;
       uint32_t accphase = 0;
       int cur_doc = -1;
+      int n_doc_warps = 0;   // epilogue warps holding an unmasked query row of the current document
       float qm_i = 0.f;
 
       for (; tw.valid(); tw.next()) {
@@ -516,6 +516,12 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             }
           }
           qm_i = S->qm[qi];   // written before the barrier above
+          // query rows past the last unmasked one contribute exactly 0 to every window (the gate q_mask[i] of :248):
+          // the warps that hold only such rows sit phase B out -- MSMARCO queries fill a fraction of the Lq slots
+          int q_hi = 0;
+          for (int i = kMaxLq - 1; i >= 0; --i)
+            if (S->qm[i] != 0.f) { q_hi = i + 1; break; }
+          n_doc_warps = (q_hi * P.K + 31) >> 5;
         }
 
         // ---- phase A: accumulator -> cosine tile -------------------------------------------------------------
@@ -571,7 +577,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         named_bar_sync(3, kEpiThreads);
         // ---- phase B: activations, block prefix / suffix, windows ------------------------------------------------
-        if (ew < n_act_warps) {
+        if (ew < n_doc_warps) {
           if (tw.halo) {
             // halo tile: only the suffix sums of its last block are wanted
             const float2* cblk = reinterpret_cast<const float2*>(cs + qi * kCsStride + 2 * kBlk * (kBlocks - 1));
@@ -656,7 +662,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           const int w = t * kTilePairs - (kBlk - 1) + et;
           if (w >= 0 && w < P.W) {
             float s = 0.f;
-            for (int ww = 0; ww < n_act_warps; ++ww) s += S->part[ww][et];
+            for (int ww = 0; ww < n_doc_warps; ++ww) s += S->part[ww][et];
             P.window_score[(int64_t)b * P.W + w] = s;
           }
         }
