@@ -222,10 +222,37 @@ struct TileWalk {
   }
 };
 
+// MMB200_ENABLE_PROF builds (python -m matchmaker_b200.build --prof) + MMB200_TKL_TS_PROF=1: one thread per role of CTA 0
+// accumulates the cycles it spends in each wait / phase; printed by the launcher.  Compiled out of the product build.
+#ifdef MMB200_ENABLE_PROF
+#define TKL_T(slot, stmt)                    \
+  do {                                       \
+    const long long t0_ = clock64();         \
+    stmt;                                    \
+    pc[slot] += clock64() - t0_;             \
+  } while (0)
+#define TKL_MARK(slot)                       \
+  do {                                       \
+    const long long now_ = clock64();        \
+    pc[slot] += now_ - t_mark;               \
+    t_mark = now_;                           \
+  } while (0)
+#else
+#define TKL_T(slot, stmt) stmt
+#define TKL_MARK(slot) \
+  do {                 \
+  } while (0)
+#endif
+
 template <int SAT>
 __global__ void __launch_bounds__(kThreads, 1)
 tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, TklParams P,
-              int n_raw, int fallback_available) {
+              int n_raw, int fallback_available, long long* prof) {
+#ifdef MMB200_ENABLE_PROF
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long t_mark = clock64();
+  const long long t_start = t_mark;
+#endif
   extern __shared__ uint8_t smem_raw[];
   if (P.plan[0] != 1) {
     if (!fallback_available && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -280,7 +307,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         const uint32_t bytes = (uint32_t)(n_present * kSlotBytes + kQxBytes);
         for (int ck = 0; ck < nch; ++ck) {
-          mbar_wait<true>(&S->raw_empty[stage], phase ^ 1u);
+          TKL_T(0, mbar_wait<true>(&S->raw_empty[stage], phase ^ 1u));
           uint8_t* st = raws + (size_t)stage * kRawBytes;
           mbar_arrive_expect_tx(&S->raw_full[stage], bytes);
 #pragma unroll
@@ -300,12 +327,12 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       int stage = 0, acc = 0;
       uint32_t phase = 0, accphase = 0;
       for (; tw.valid(); tw.next()) {
-        mbar_wait<true>(&S->accempty[acc], accphase ^ 1u);
+        TKL_T(0, mbar_wait<true>(&S->accempty[acc], accphase ^ 1u));
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + (uint32_t)(kAccCol0 + acc * kNq);
         for (int ck = 0; ck < nch; ++ck) {
           const int ksteps = (min(32, P.D - ck * 32) + 7) >> 3;
-          mbar_wait<true>(&S->op_full[stage], phase);
+          TKL_T(1, mbar_wait<true>(&S->op_full[stage], phase));
           tc_fence_after_sync();
           const uint32_t abase = tmem_base + (uint32_t)(stage * 64);
           const uint64_t b0 = make_sw128_kmajor_desc(smem_u32(qring + (size_t)stage * kQopBytes));
@@ -341,7 +368,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       for (; tw.valid(); tw.next()) {
         float ss[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         for (int ck = 0; ck < nch; ++ck) {
-          mbar_wait<true>(&S->raw_full[rs_], rphase);
+          TKL_T(0, mbar_wait<true>(&S->raw_full[rs_], rphase));
           const uint8_t* xq = raws + (size_t)rs_ * kRawBytes + kDxBytes;
           float4 x[5];
 #pragma unroll
@@ -350,7 +377,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             x[j] = *reinterpret_cast<const float4*>(xq + row * 128 + ((c ^ (row & 7)) << 4));
             ss[j] = fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, fmaf(x[j].z, x[j].z, fmaf(x[j].w, x[j].w, ss[j]))));
           }
-          mbar_wait<true>(&S->op_empty[os_], ophase ^ 1u);
+          TKL_T(1, mbar_wait<true>(&S->op_empty[os_], ophase ^ 1u));
           uint8_t* qo = qring + (size_t)os_ * kQopBytes;
 #pragma unroll
           for (int j = 0; j < 5; ++j) {
@@ -397,7 +424,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         float4 ss4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int ck = 0; ck < nch; ++ck) {
           const bool second = P.D - ck * 32 > 16;   // columns 16..31 of this chunk hold data (warp-uniform)
-          mbar_wait<true>(&S->raw_full[rs_], rphase);
+          TKL_T(0, mbar_wait<true>(&S->raw_full[rs_], rphase));
           const uint8_t* xrow = raws + (size_t)rs_ * kRawBytes + row * 128;
           float4 x[4];
 #pragma unroll
@@ -407,7 +434,7 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             const float4 v = x[c];
             ss4.x = fmaf(v.x, v.x, ss4.x); ss4.y = fmaf(v.y, v.y, ss4.y); ss4.z = fmaf(v.z, v.z, ss4.z); ss4.w = fmaf(v.w, v.w, ss4.w);
           }
-          mbar_wait<true>(&S->op_empty[os_], ophase ^ 1u);
+          TKL_T(1, mbar_wait<true>(&S->op_empty[os_], ophase ^ 1u));
           tc_fence_after_sync();
           const uint32_t taddr = trow + (uint32_t)(os_ * 64);
           {   // columns 0..15 of the chunk
@@ -533,7 +560,9 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           present = pk >= 0;
           if (present) draw = dmt != MMB200_MASK_NONE ? mask_raw(P.chunk_mask, dmt, (int64_t)pk * kChunk + (row % kChunk)) : 1;
         }
+        TKL_MARK(7);   // bookkeeping between tiles, document switch
         mbar_wait<true>(&S->accfull[acc_slot], accphase);
+        TKL_MARK(0);   // wait for the accumulator
         tc_fence_after_sync();
         {
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(kAccCol0 + acc_slot * kNq + 10 * cg);
@@ -563,7 +592,9 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         if (++acc_slot == kAcc) { acc_slot = 0; accphase ^= 1u; }
         if (++nr == kNormRing) nr = 0;
+        TKL_MARK(1);   // phase A
         named_bar_sync(2, kEpiThreads);
+        TKL_MARK(2);   // barrier 2
         // ---- token count of the window ending at each pair of this tile (sigir20_tkl.py:210 under "cover") ----
         if (et < kTilePairs) {
           const int last = t * kTileRows + 2 * et + 1;   // last position of the window ending at pair et
@@ -575,7 +606,9 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           }
           S->lenw[et / kBlk][et % kBlk] = (uint16_t)(16 * (int)n);
         }
+        TKL_MARK(3);   // token counts
         named_bar_sync(3, kEpiThreads);
+        TKL_MARK(2);
         // ---- phase B: activations, block prefix / suffix, windows ------------------------------------------------
         if (ew < n_doc_warps) {
           if (tw.halo) {
@@ -657,7 +690,9 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             }
           }
         }
+        TKL_MARK(4);   // phase B
         named_bar_sync(4, kEpiThreads);
+        TKL_MARK(5);   // barrier 4
         if (!tw.halo && et < kTilePairs) {
           const int w = t * kTilePairs - (kBlk - 1) + et;
           if (w >= 0 && w < P.W) {
@@ -670,6 +705,13 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
   }
 
+#ifdef MMB200_ENABLE_PROF
+  if (prof && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == kFirstDocWarp || warp == kFirstEpiWarp)) {
+    const int role = warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : warp == kFirstDocWarp ? 3 : 4;
+    for (int i = 0; i < 8; ++i) prof[role * 9 + i] = pc[i];
+    prof[role * 9 + 8] = clock64() - t_start;
+  }
+#endif
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
@@ -723,6 +765,14 @@ int tkl_window_ts_launch(TklParams& P, const DeviceInfo& dev, cudaStream_t strea
   MMB_CHECK_CUDA(cudaMemsetAsync(P.window_score, 0, (size_t)P.B * P.W * sizeof(float), stream));
   const int grid = dev.sm_count;
   const int fallback = P.segs > 0 ? 1 : 0;
+  long long* prof = nullptr;
+#ifdef MMB200_ENABLE_PROF
+  const bool do_prof = getenv("MMB200_TKL_TS_PROF") != nullptr;
+  if (do_prof) {
+    MMB_CHECK_CUDA(cudaMalloc(&prof, 45 * sizeof(long long)));
+    MMB_CHECK_CUDA(cudaMemset(prof, 0, 45 * sizeof(long long)));
+  }
+#endif
   static bool attr_set[2][64] = {};
   const int di = dev.device & 63;
   if (P.saturation == 0) {
@@ -730,15 +780,28 @@ int tkl_window_ts_launch(TklParams& P, const DeviceInfo& dev, cudaStream_t strea
       MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev.max_smem_optin));
       attr_set[0][di] = true;
     }
-    tkl_ts_kernel<0><<<grid, kThreads, smem, stream>>>(tq, tc, P, n_raw, fallback);
+    tkl_ts_kernel<0><<<grid, kThreads, smem, stream>>>(tq, tc, P, n_raw, fallback, prof);
   } else {
     if (!attr_set[1][di]) {
       MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev.max_smem_optin));
       attr_set[1][di] = true;
     }
-    tkl_ts_kernel<1><<<grid, kThreads, smem, stream>>>(tq, tc, P, n_raw, fallback);
+    tkl_ts_kernel<1><<<grid, kThreads, smem, stream>>>(tq, tc, P, n_raw, fallback, prof);
   }
   MMB_CHECK_CUDA(cudaGetLastError());
+#ifdef MMB200_ENABLE_PROF
+  if (do_prof) {
+    long long h[45];
+    MMB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    MMB_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost));
+    MMB_CHECK_CUDA(cudaFree(prof));
+    fprintf(stderr,
+            "tkl_ts_prof cycles (CTA 0): tma total %lld wait_raw_empty %lld | mma total %lld wait_accempty %lld wait_op_full %lld | qconv total %lld "
+            "wait_raw_full %lld wait_op_empty %lld | dconv total %lld wait_raw_full %lld wait_op_empty %lld | epi total %lld wait_accfull %lld "
+            "phaseA %lld barriers23 %lld counts %lld phaseB %lld barrier4 %lld between %lld\n",
+            h[8], h[0], h[17], h[9], h[10], h[26], h[18], h[19], h[35], h[27], h[28], h[44], h[36], h[37], h[38], h[39], h[40], h[41], h[43]);
+  }
+#endif
   *handled = true;
   return MMB200_OK;
 }
