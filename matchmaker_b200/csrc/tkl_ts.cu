@@ -496,6 +496,18 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       for (int r = 0; r < kBlk; ++r) suf[r] = 0.f;
       int acc_slot = 0, nr = 0;
       uint32_t accphase = 0;
+      auto fetch_mask = [&](int bb, int tt, bool& pres, uint64_t& raw) {
+        pres = false;
+        raw = 0;
+        if (row < kTileRows) {
+          const int c = tt * kTileSlots + row / kChunk;
+          const int pk = c < P.C ? P.slot_to_packed[(int64_t)bb * P.C + c] : -1;
+          pres = pk >= 0;
+          if (pres) raw = dmt != MMB200_MASK_NONE ? mask_raw(P.chunk_mask, dmt, (int64_t)pk * kChunk + (row % kChunk)) : 1;
+        }
+      };
+      bool have_next = false, nxt_present = false;
+      uint64_t nxt_draw = 0;
       int cur_doc = -1;
       int n_doc_warps = 0;   // epilogue warps holding an unmasked query row of the current document
       float qm_i = 0.f;
@@ -509,19 +521,29 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           named_bar_sync(1, kEpiThreads);   // nobody still reads the previous document's table / qm
           if (et < kMaxLq) S->qm[et] = (et < P.Lq && mask_at(P.q_mask, qmt, (int64_t)b * P.Lq + et)) ? 1.f : 0.f;
           if (SAT == 0) {
-            for (int i = ew; i < kMaxLq; i += kEpiWarps) {
-              float rd = 0.f;
-              if (i < P.Lq) {
-                const float4* qrow = reinterpret_cast<const float4*>(P.q + ((int64_t)b * P.Lq + i) * P.D);
-                const float4* wr = reinterpret_cast<const float4*>(P.sat_red_w);
-                for (int c4 = lane; c4 < (P.D >> 2); c4 += 32) {
-                  const float4 v = __ldg(qrow + c4), w = __ldg(wr + c4);
-                  rd = fmaf(v.x, w.x, rd); rd = fmaf(v.y, w.y, rd); rd = fmaf(v.z, w.z, rd); rd = fmaf(v.w, w.w, rd);
-                }
+            // the warp's rows ew, ew + 16, ew + 32 side by side: their loads are independent and in flight together (one
+            // global-memory latency per document switch instead of one per row and 128-byte step)
+            float rd[3] = {0.f, 0.f, 0.f};
+            const float4* wr = reinterpret_cast<const float4*>(P.sat_red_w);
+#pragma unroll 2
+            for (int c4 = lane; c4 < (P.D >> 2); c4 += 32) {
+              const float4 w = __ldg(wr + c4);
+              float4 v[3];
+#pragma unroll
+              for (int a = 0; a < 3; ++a) {
+                const int i = ew + kEpiWarps * a;
+                v[a] = i < P.Lq ? __ldg(reinterpret_cast<const float4*>(P.q + ((int64_t)b * P.Lq + i) * P.D) + c4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
               }
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) rd += __shfl_xor_sync(0xffffffffu, rd, o);
-              if (lane == 0) S->red[i] = rd;
+              for (int a = 0; a < 3; ++a)
+                rd[a] = fmaf(v[a].x, w.x, fmaf(v[a].y, w.y, fmaf(v[a].z, w.z, fmaf(v[a].w, w.w, rd[a]))));
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) rd[a] += __shfl_xor_sync(0xffffffffu, rd[a], o);
+              if (lane == 0 && ew + kEpiWarps * a < kMaxLq) S->red[ew + kEpiWarps * a] = rd[a];
             }
           }
           named_bar_sync(1, kEpiThreads);
@@ -552,14 +574,11 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
 
         // ---- phase A: accumulator -> cosine tile -------------------------------------------------------------
-        uint64_t draw = 0;
-        bool present = false;
-        if (row < kTileRows) {
-          const int c = t * kTileSlots + row / kChunk;
-          const int pk = c < P.C ? P.slot_to_packed[(int64_t)b * P.C + c] : -1;
-          present = pk >= 0;
-          if (present) draw = dmt != MMB200_MASK_NONE ? mask_raw(P.chunk_mask, dmt, (int64_t)pk * kChunk + (row % kChunk)) : 1;
-        }
+        // this position's mask word was fetched while the previous tile was in phase B (two dependent global loads --
+        // slot map, then mask -- that the accumulator wait no longer hides: the producers run ahead of the epilogue)
+        if (!have_next) fetch_mask(b, t, nxt_present, nxt_draw);
+        const uint64_t draw = nxt_draw;
+        const bool present = nxt_present;
         TKL_MARK(7);   // bookkeeping between tiles, document switch
         mbar_wait<true>(&S->accfull[acc_slot], accphase);
         TKL_MARK(0);   // wait for the accumulator
@@ -592,19 +611,29 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         if (++acc_slot == kAcc) { acc_slot = 0; accphase ^= 1u; }
         if (++nr == kNormRing) nr = 0;
+        {   // mask word of this position in the NEXT tile: in flight during the token counts and phase B
+          TileWalk tn = tw;
+          tn.next();
+          have_next = tn.valid();
+          if (have_next) fetch_mask(tn.b, tn.t, nxt_present, nxt_draw);
+        }
         TKL_MARK(1);   // phase A
         named_bar_sync(2, kEpiThreads);
         TKL_MARK(2);   // barrier 2
         // ---- token count of the window ending at each pair of this tile (sigir20_tkl.py:210 under "cover") ----
-        if (et < kTilePairs) {
-          const int last = t * kTileRows + 2 * et + 1;   // last position of the window ending at pair et
+        if (et < 8 * kTilePairs) {   // eight threads per window, four positions each, three shuffle steps
+          const int wl = et >> 3, sub = et & 7;
+          const int last = t * kTileRows + 2 * wl + 1;   // last position of the window ending at pair wl
           float n = 0.f;
-#pragma unroll 6
-          for (int u = 0; u < kWindow; ++u) {
+#pragma unroll
+          for (int u = sub; u < kWindow; u += 8) {
             const int pos = last - u;
             if (pos >= 0) n += S->dmring[pos & 255];
           }
-          S->lenw[et / kBlk][et % kBlk] = (uint16_t)(16 * (int)n);
+          n += __shfl_xor_sync(0xffffffffu, n, 1);
+          n += __shfl_xor_sync(0xffffffffu, n, 2);
+          n += __shfl_xor_sync(0xffffffffu, n, 4);
+          if (sub == 0) S->lenw[wl / kBlk][wl % kBlk] = (uint16_t)(16 * (int)n);
         }
         TKL_MARK(3);   // token counts
         named_bar_sync(3, kEpiThreads);
