@@ -24,7 +24,8 @@ struct TklParams {
   int32_t segs, chunks_per_seg;
   // plan written on the device by tkl_plan_kernel (tkl_ts.cu); nullptr when the tensor-core path is not in play
   const int32_t* plan;       // [0] = 1 when every cosine in [-1, 1] activates at least one kernel ("cover"),
-                             // [1] = total tiles, [2 + b] = tiles before document b (B + 1 entries)
+                             // [1] = total tiles, [2 + b] = tiles before document b (B + 1 entries), then the cost prefix and the
+                             // first tile of every CTA (layout in tkl_ts.cu:tkl_plan_kernel)
 };
 
 struct DeviceInfo;

@@ -119,17 +119,52 @@ __device__ __forceinline__ void split4(const float4 v, uint32_t* hi, uint32_t* l
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// plan: tiles per document (prefix sums) + the "cover" test of the kernel set.  One block.
-// plan[0] = cover, plan[1] = total tiles, plan[2 + b] = tiles before document b (b = 0..B).
+// plan: tiles per document (prefix sums), the "cover" test of the kernel set, and the share of every CTA.  One block.
+//   plan[0] = cover, plan[1] = total tiles, plan[2 + b] = tiles before document b (b = 0..B),
+//   plan[3 + B + b] = cost before document b (b = 0..B), plan[4 + 2B + x] = first tile of CTA x (x = 0..grid).
+// A tile's cost is counted in warp-tiles of epilogue work: kTileFixedCost for everything that does not depend on the
+// query (convert, MMA, phase A, barriers; from the per-role profile) plus one per epilogue warp that holds an unmasked
+// query row -- short queries leave most of phase B idle, so their documents' tiles are cheaper and a CTA takes more.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tkl_plan_kernel(const int32_t* __restrict__ slot_to_packed, int64_t B, int C,
-                                                        const float* __restrict__ mu, const float* __restrict__ sigma, int K,
-                                                        int force_cover, int32_t* __restrict__ plan) {
+constexpr int kTileFixedCost = 17;
+
+__device__ __forceinline__ void block_exclusive_scan_inplace(int32_t* v, int64_t n, int* sums, int* carry, int32_t* total_out) {
+  const int t = threadIdx.x;
+  if (t == 0) *carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + t;
+    const int x = i < n ? v[i] : 0;
+    sums[t] = x;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int u = t >= o ? sums[t - o] : 0;
+      __syncthreads();
+      sums[t] += u;
+      __syncthreads();
+    }
+    if (i < n) v[i] = *carry + sums[t] - x;
+    __syncthreads();
+    if (t == 1023) *carry += sums[1023];
+    __syncthreads();
+  }
+  if (t == 0) { *total_out = *carry; v[n] = *carry; }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) tkl_plan_kernel(const int32_t* __restrict__ slot_to_packed, const void* __restrict__ q_mask,
+                                                        int mask_dtype, int64_t B, int C, int Lq, const float* __restrict__ mu,
+                                                        const float* __restrict__ sigma, int K, int grid, int force_cover,
+                                                        int32_t* __restrict__ plan) {
   __shared__ int sums[1024];
   __shared__ int carry;
+  __shared__ int total_tiles, total_cost;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tiles_max = (C + kTileSlots - 1) / kTileSlots;
-  // pass 1: tiles of every document (one warp per document, coalesced reads of its C slots) -> plan[2 + b]
+  int32_t* tile_pre = plan + 2;
+  int32_t* cost_pre = plan + 3 + B;
+  int32_t* cta_start = plan + 4 + 2 * B;
+  // pass 1: tiles and cost of every document (one warp per document, coalesced reads of its C slots and Lq mask words)
   for (int64_t b = warp; b < B; b += 32) {
     int c_last = -1;
     for (int c0 = 0; c0 < C; c0 += 32) {
@@ -138,31 +173,42 @@ __global__ void __launch_bounds__(1024) tkl_plan_kernel(const int32_t* __restric
       const unsigned m = __ballot_sync(0xffffffffu, packed);
       if (m) c_last = c0 + 31 - __clz(m);
     }
-    // windows overlapping a packed chunk end at the latest in slot c_last + 1
-    if (lane == 0) plan[2 + b] = c_last < 0 ? 0 : min(tiles_max, (c_last + 1) / kTileSlots + 1);
-  }
-  if (t == 0) carry = 0;
-  __syncthreads();
-  // pass 2: exclusive prefix sums in place, 1024 documents per round
-  for (int64_t base = 0; base < B; base += 1024) {
-    const int64_t b = base + t;
-    const int v = b < B ? plan[2 + b] : 0;
-    sums[t] = v;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const int u = t >= o ? sums[t - o] : 0;
-      __syncthreads();
-      sums[t] += u;
-      __syncthreads();
+    int q_hi = 0;
+    for (int i0 = 0; i0 < Lq; i0 += 32) {
+      const int i = i0 + lane;
+      const bool live = i < Lq && mask_at(q_mask, q_mask ? mask_dtype : MMB200_MASK_NONE, b * Lq + i);
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if (m) q_hi = i0 + 32 - __clz(m);
     }
-    if (b < B) plan[2 + b] = carry + sums[t] - v;
-    __syncthreads();
-    if (t == 1023) carry += sums[1023];
-    __syncthreads();
+    if (lane == 0) {
+      // windows overlapping a packed chunk end at the latest in slot c_last + 1
+      const int tiles = c_last < 0 ? 0 : min(tiles_max, (c_last + 1) / kTileSlots + 1);
+      tile_pre[b] = tiles;
+      cost_pre[b] = tiles * (kTileFixedCost + ((q_hi * K + 31) >> 5));
+    }
+  }
+  __syncthreads();
+  block_exclusive_scan_inplace(tile_pre, B, sums, &carry, &total_tiles);
+  block_exclusive_scan_inplace(cost_pre, B, sums, &carry, &total_cost);
+  // pass 3: CTA x starts at the tile where the cumulative cost reaches x / grid of the total
+  for (int x = t; x <= grid; x += 1024) {
+    int start = total_tiles;
+    if (x < grid && total_tiles > 0) {
+      const long long target = (long long)total_cost * x / grid;
+      int64_t lo = 0, hi = B - 1;   // last document whose cost prefix is <= target
+      while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (cost_pre[mid] <= target) lo = mid; else hi = mid - 1;
+      }
+      const int tiles = tile_pre[lo + 1] - tile_pre[lo];
+      const int dcost = cost_pre[lo + 1] - cost_pre[lo];
+      const int per_tile = tiles > 0 ? dcost / tiles : 1;
+      start = tile_pre[lo] + (tiles > 0 ? min(tiles, (int)((target - cost_pre[lo] + per_tile - 1) / per_tile)) : 0);
+    }
+    cta_start[x] = start;
   }
   if (t == 0) {
-    plan[1] = carry;
-    plan[2 + B] = carry;
+    plan[1] = total_tiles;
     // activation k is non-zero (ex2.approx.ftz) for |c - mu_k| * a_k <= sqrt(126); 11.0 leaves a margin.  Sweep the
     // union of the intervals over [-1.01, 1.01].
     float x = -1.01f;
@@ -191,10 +237,9 @@ struct TileWalk {
   bool halo;
   __device__ __forceinline__ bool init(const int32_t* plan, int B, int cta, int ncta) {
     pre = plan + 2;
-    const int total = plan[1];
-    const int per = (total + ncta - 1) / ncta;
-    g = cta * per;
-    g_end = min(total, g + per);
+    const int32_t* cta_start = plan + 4 + 2 * B;   // shares of equal COST (tkl_plan_kernel), monotone in the CTA index
+    g = cta_start[cta];
+    g_end = cta_start[cta + 1];
     if (g >= g_end) return false;
     int lo = 0, hi = B - 1;   // last document with pre[b] <= g ...
     while (lo < hi) {
@@ -782,17 +827,18 @@ int tkl_window_ts_launch(TklParams& P, const DeviceInfo& dev, cudaStream_t strea
       return rc;
   }
   int32_t* plan = nullptr;
-  MMB_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&plan), (size_t)(P.B + 3) * sizeof(int32_t), stream));
+  const int grid = dev.sm_count;
+  MMB_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&plan), (size_t)(2 * P.B + 6 + grid) * sizeof(int32_t), stream));
   int force = 0;
 #ifdef MMB200_ENABLE_PROF
   if (const char* e = getenv("MMB200_TKL_COVER")) force = atoi(e);  // 1 / -1: force the answer of the cover test
 #endif
-  tkl_plan_kernel<<<1, 1024, 0, stream>>>(P.slot_to_packed, P.B, P.C, P.mu, P.sigma, P.K, force, plan);
+  tkl_plan_kernel<<<1, 1024, 0, stream>>>(P.slot_to_packed, P.q_mask, P.mask_dtype, P.B, P.C, P.Lq, P.mu, P.sigma, P.K, grid,
+                                          force, plan);
   MMB_CHECK_CUDA(cudaGetLastError());
   P.plan = plan;
   *plan_out = plan;
   MMB_CHECK_CUDA(cudaMemsetAsync(P.window_score, 0, (size_t)P.B * P.W * sizeof(float), stream));
-  const int grid = dev.sm_count;
   const int fallback = P.segs > 0 ? 1 : 0;
   long long* prof = nullptr;
 #ifdef MMB200_ENABLE_PROF
