@@ -279,83 +279,113 @@ __global__ void __launch_bounds__(kThreads) tkl_window_kernel(TklParams P, long 
   }
 }
 
-// One warp per document: sentinel, 3 greedy hills, neighbours, weighted sum (sigir20_tkl.py:254-286).
-__global__ void __launch_bounds__(128) tkl_hills_kernel(const float* window_score, float* orig_score,
-                                                        const float* __restrict__ chunk_scoring,
-                                                        int64_t* __restrict__ top_idx, float* __restrict__ top15,
-                                                        float* __restrict__ score, int64_t B, int W) {
-  extern __shared__ float work[];  // [4 warps][W]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * 4 + warp;
-  if (b >= B) return;
-  const float* win = window_score + b * W;   // may alias orig_score (in-place use)
-  float* ws = orig_score + b * W;
-  float* wk = work + (size_t)warp * W;
-  for (int w = lane; w < W; w += 32) {
-    float v = win[w];
-    if (v == 0.f) v = -9900.f;  // :257
-    ws[w] = v;
-    wk[w] = v;
-  }
-  __syncwarp();
-  int best[3];
-  for (int c = 0; c < 3; ++c) {
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int w = lane; w < W; w += 32) {
-      const float v = wk[w];
-      if (v > bv) { bv = v; bi = w; }  // ascending scan keeps the first maximum
+// One block per document: sentinel, 3 greedy hills, neighbours, weighted sum (sigir20_tkl.py:254-286).  The window
+// scores live in shared memory for the whole selection (round 1 walked them in global memory with one warp per document:
+// 31 dependent global round trips per pass, 26 us for 128 documents; this version is bound by one read and one write).
+constexpr int kHillThreads = 256;
+
+__global__ void __launch_bounds__(kHillThreads) tkl_hills_kernel(const float* window_score, float* orig_score,
+                                                                const float* __restrict__ chunk_scoring,
+                                                                int64_t* __restrict__ top_idx, float* __restrict__ top15,
+                                                                float* __restrict__ score, int64_t B, int W) {
+  extern __shared__ float hsm[];
+  float* orig = hsm;            // [W] scores with the -9900 sentinel (what the reference indexes for the neighbours)
+  float* wk = hsm + W;          // [W] working copy, suppressed regions overwritten
+  __shared__ float red_v[kHillThreads / 32];
+  __shared__ int red_i[kHillThreads / 32];
+  __shared__ int best_s[3];
+  __shared__ float t15[15];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const float* win = window_score + b * W;   // may alias orig_score (in-place use): read completely before any write
+    __syncthreads();
+    for (int w = t; w < W; w += kHillThreads) {
+      float v = win[w];
+      if (v == 0.f) v = -9900.f;  // :257
+      orig[w] = v;
+      wk[w] = v;
     }
+    __syncthreads();
+    for (int c = 0; c < 3; ++c) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int w = t; w < W; w += kHillThreads) {
+        const float v = wk[w];
+        if (v > bv) { bv = v; bi = w; }  // ascending scan keeps the first maximum
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+      __syncthreads();
+      if (t == 0) {
+        float fv = red_v[0];
+        int fi = red_i[0];
+        for (int x = 1; x < kHillThreads / 32; ++x)
+          if (red_v[x] > fv || (red_v[x] == fv && red_i[x] < fi)) { fv = red_v[x]; fi = red_i[x]; }
+        best_s[c] = fi;
+      }
+      __syncthreads();
+      const int bi_all = best_s[c];
+      for (int w = t; w < W; w += kHillThreads)
+        if (fabsf((float)(w - bi_all)) < 15.0f) wk[w] = -10001.f - (float)c;  // |r - best| < window/2 (:270-271)
+      __syncthreads();
     }
-    best[c] = bi;
-    for (int w = lane; w < W; w += 32)
-      if (fabsf((float)(w - bi)) < 15.0f) wk[w] = -10001.f - (float)c;  // |r - best| < window/2 (:270-271)
-    __syncwarp();
+    if (t < 15) {
+      const int c = t % 3, off_sel = t / 3;  // cat([idx, idx-1, idx+1, idx-2, idx+2], dim=1) (:274)
+      const int off = off_sel == 0 ? 0 : (off_sel == 1 ? -1 : (off_sel == 2 ? 1 : (off_sel == 3 ? -2 : 2)));
+      int idx = best_s[c] + off;
+      idx = idx < 0 ? 0 : (idx >= W ? W - 1 : idx);
+      float v = orig[idx];
+      if (v <= -9900.f) v = 0.f;  // :281
+      top15[b * 15 + t] = v;
+      t15[t] = v * chunk_scoring[t];
+    }
+    if (t < 3) top_idx[b * 3 + t] = best_s[t];
+    __syncthreads();
+    if (t == 0) {  // fixed-order sum over the 15 terms
+      float tot = 0.f;
+      for (int l = 0; l < 15; ++l) tot += t15[l];
+      score[b] = tot;
+    }
+    for (int w = t; w < W; w += kHillThreads) {
+      const float v = orig[w];
+      orig_score[b * W + w] = v <= -9900.f ? 0.f : v;  // :284 (the reference's returned "orig_score")
+    }
   }
-  if (lane < 15) {
-    const int c = lane % 3, off_sel = lane / 3;  // cat([idx, idx-1, idx+1, idx-2, idx+2], dim=1) (:274)
-    const int off = off_sel == 0 ? 0 : (off_sel == 1 ? -1 : (off_sel == 2 ? 1 : (off_sel == 3 ? -2 : 2)));
-    int idx = best[c] + off;
-    idx = idx < 0 ? 0 : (idx >= W ? W - 1 : idx);
-    float v = ws[idx];
-    if (v <= -9900.f) v = 0.f;  // :281
-    top15[b * 15 + lane] = v;
-  }
-  if (lane < 3) top_idx[b * 3 + lane] = best[lane];
-  __syncwarp();
-  float part = lane < 15 ? top15[b * 15 + lane] * chunk_scoring[lane] : 0.f;
-  // fixed-order sum over the 15 terms (lane 0 adds them sequentially)
-  float tot = 0.f;
-  for (int l = 0; l < 15; ++l) tot += __shfl_sync(0xffffffffu, part, l);
-  if (lane == 0) score[b] = tot;
-  __syncwarp();
-  for (int w = lane; w < W; w += 32)
-    if (ws[w] <= -9900.f) ws[w] = 0.f;  // :284 (the reference's returned "orig_score")
 }
 
 // slot_to_packed[s] = (number of packed slots before s) if packed[s] else -1.  One block; n = B * C is small.
 __global__ void __launch_bounds__(1024) tkl_slot_map_kernel(const uint8_t* __restrict__ packed, int64_t n,
                                                             int32_t* __restrict__ slot_to_packed) {
-  __shared__ int sums[1024];
-  const int t = threadIdx.x;
+  __shared__ int wsum[32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int64_t per = (n + 1023) / 1024;
   const int64_t lo = min(n, (int64_t)t * per), hi = min(n, lo + per);
   int local = 0;
   for (int64_t i = lo; i < hi; ++i) local += packed[i] ? 1 : 0;
-  sums[t] = local;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int v = t >= o ? sums[t - o] : 0;
-    __syncthreads();
-    sums[t] += v;
-    __syncthreads();
+  int incl = local;   // inclusive scan over the block: shuffles inside the warp, one shared-memory hop across warps
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
   }
-  int run = sums[t] - local;
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += u;
+    }
+    wsum[lane] = w;
+  }
+  __syncthreads();
+  int run = incl - local + (warp > 0 ? wsum[warp - 1] : 0);
   for (int64_t i = lo; i < hi; ++i) slot_to_packed[i] = packed[i] ? run++ : -1;
 }
 
@@ -475,10 +505,10 @@ extern "C" int mmb200_tkl_top_hills(const float* window_score, float* orig_score
     set_error("matchmaker_b200 kernels are built for sm_100a only");
     return MMB200_ERR_UNSUPPORTED;
   }
-  const size_t smem = (size_t)4 * W * sizeof(float);
+  const size_t smem = (size_t)2 * W * sizeof(float);
   MMB_REQUIRE(smem <= (size_t)dev.max_smem_optin, "too many windows for the hills kernel");
   MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_hills_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tkl_hills_kernel<<<(unsigned)((B + 3) / 4), 128, smem, static_cast<cudaStream_t>(stream_)>>>(
+  tkl_hills_kernel<<<(unsigned)std::min<int64_t>(B, (int64_t)dev.sm_count * 8), kHillThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
       window_score, orig_score, chunk_scoring, top_idx, top15, score, B, W);
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;

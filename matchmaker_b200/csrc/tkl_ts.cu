@@ -128,24 +128,37 @@ __device__ __forceinline__ void split4(const float4 v, uint32_t* hi, uint32_t* l
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTileFixedCost = 17;
 
-__device__ __forceinline__ void block_exclusive_scan_inplace(int32_t* v, int64_t n, int* sums, int* carry, int32_t* total_out) {
-  const int t = threadIdx.x;
+// exclusive prefix sums of v[0..n) in place, v[n] = total; 1024 threads, 1024 elements per round: shuffles inside the
+// warp, one shared-memory hop across warps (three barriers per round instead of twenty)
+__device__ __forceinline__ void block_exclusive_scan_inplace(int32_t* v, int64_t n, int* wsum, int* carry, int32_t* total_out) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t == 0) *carry = 0;
   __syncthreads();
   for (int64_t base = 0; base < n; base += 1024) {
     const int64_t i = base + t;
     const int x = i < n ? v[i] : 0;
-    sums[t] = x;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const int u = t >= o ? sums[t - o] : 0;
-      __syncthreads();
-      sums[t] += u;
-      __syncthreads();
+    int incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
     }
-    if (i < n) v[i] = *carry + sums[t] - x;
+    if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    if (t == 1023) *carry += sums[1023];
+    if (warp == 0) {
+      int w = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += u;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const int c0 = *carry;
+    if (i < n) v[i] = c0 + incl - x + (warp > 0 ? wsum[warp - 1] : 0);
+    __syncthreads();
+    if (t == 0) *carry = c0 + wsum[31];
     __syncthreads();
   }
   if (t == 0) { *total_out = *carry; v[n] = *carry; }
