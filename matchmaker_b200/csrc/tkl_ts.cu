@@ -172,32 +172,60 @@ __global__ void __launch_bounds__(1024) tkl_plan_kernel(const int32_t* __restric
   __shared__ int sums[1024];
   __shared__ int carry;
   __shared__ int total_tiles, total_cost;
+  __shared__ float klo[32], khi[32];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t < K && t < 32) {
+    const float h = 11.0f * sigma[t] / sqrtf(0.5f * 1.4426950408889634f);
+    klo[t] = mu[t] - h;
+    khi[t] = mu[t] + h;
+  }
   const int tiles_max = (C + kTileSlots - 1) / kTileSlots;
   int32_t* tile_pre = plan + 2;
   int32_t* cost_pre = plan + 3 + B;
   int32_t* cta_start = plan + 4 + 2 * B;
-  // pass 1: tiles and cost of every document (one warp per document, coalesced reads of its C slots and Lq mask words)
-  for (int64_t b = warp; b < B; b += 32) {
-    int c_last = -1;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-      const int c = c0 + lane;
-      const bool packed = c < C && slot_to_packed[b * C + c] >= 0;
-      const unsigned m = __ballot_sync(0xffffffffu, packed);
-      if (m) c_last = c0 + 31 - __clz(m);
+  // pass 1: tiles and cost of every document: one warp per document, four documents per warp in flight (all of their slot
+  // and mask words are requested before the first ballot -- one global-memory latency per batch, not four per document)
+  const int qmt = q_mask ? mask_dtype : MMB200_MASK_NONE;
+  const bool small = C <= 64 && Lq <= 64;
+  for (int64_t b0 = (int64_t)warp * 4; b0 < B; b0 += 128) {
+    bool pk0[4], pk1[4], lv0[4], lv1[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int64_t b = b0 + a;
+      const bool ok = small && b < B;
+      pk0[a] = ok && lane < C && slot_to_packed[b * C + lane] >= 0;
+      pk1[a] = ok && lane + 32 < C && slot_to_packed[b * C + lane + 32] >= 0;
+      lv0[a] = ok && lane < Lq && mask_at(q_mask, qmt, b * Lq + lane);
+      lv1[a] = ok && lane + 32 < Lq && mask_at(q_mask, qmt, b * Lq + lane + 32);
     }
-    int q_hi = 0;
-    for (int i0 = 0; i0 < Lq; i0 += 32) {
-      const int i = i0 + lane;
-      const bool live = i < Lq && mask_at(q_mask, q_mask ? mask_dtype : MMB200_MASK_NONE, b * Lq + i);
-      const unsigned m = __ballot_sync(0xffffffffu, live);
-      if (m) q_hi = i0 + 32 - __clz(m);
-    }
-    if (lane == 0) {
-      // windows overlapping a packed chunk end at the latest in slot c_last + 1
-      const int tiles = c_last < 0 ? 0 : min(tiles_max, (c_last + 1) / kTileSlots + 1);
-      tile_pre[b] = tiles;
-      cost_pre[b] = tiles * (kTileFixedCost + ((q_hi * K + 31) >> 5));
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int64_t b = b0 + a;
+      if (b >= B) break;   // warp-uniform
+      int c_last = -1, q_hi = 0;
+      if (small) {
+        const unsigned m0 = __ballot_sync(0xffffffffu, pk0[a]), m1 = __ballot_sync(0xffffffffu, pk1[a]);
+        c_last = m1 ? 63 - __clz(m1) : (m0 ? 31 - __clz(m0) : -1);
+        const unsigned q0 = __ballot_sync(0xffffffffu, lv0[a]), q1 = __ballot_sync(0xffffffffu, lv1[a]);
+        q_hi = q1 ? 64 - __clz(q1) : (q0 ? 32 - __clz(q0) : 0);
+      } else {
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          const int c = c0 + lane;
+          const unsigned m = __ballot_sync(0xffffffffu, c < C && slot_to_packed[b * C + c] >= 0);
+          if (m) c_last = c0 + 31 - __clz(m);
+        }
+        for (int i0 = 0; i0 < Lq; i0 += 32) {
+          const int i = i0 + lane;
+          const unsigned m = __ballot_sync(0xffffffffu, i < Lq && mask_at(q_mask, qmt, b * Lq + i));
+          if (m) q_hi = i0 + 32 - __clz(m);
+        }
+      }
+      if (lane == 0) {
+        // windows overlapping a packed chunk end at the latest in slot c_last + 1
+        const int tiles = c_last < 0 ? 0 : min(tiles_max, (c_last + 1) / kTileSlots + 1);
+        tile_pre[b] = tiles;
+        cost_pre[b] = tiles * (kTileFixedCost + ((q_hi * K + 31) >> 5));
+      }
     }
   }
   __syncthreads();
@@ -223,15 +251,13 @@ __global__ void __launch_bounds__(1024) tkl_plan_kernel(const int32_t* __restric
   if (t == 0) {
     plan[1] = total_tiles;
     // activation k is non-zero (ex2.approx.ftz) for |c - mu_k| * a_k <= sqrt(126); 11.0 leaves a margin.  Sweep the
-    // union of the intervals over [-1.01, 1.01].
+    // union of the intervals [klo, khi] (computed by K threads at the start) over [-1.01, 1.01].
     float x = -1.01f;
     bool ok = true;
     while (x < 1.01f) {
       float reach = x;
-      for (int k = 0; k < K; ++k) {
-        const float h = 11.0f * sigma[k] / sqrtf(0.5f * 1.4426950408889634f);
-        if (mu[k] - h <= x && mu[k] + h > reach) reach = mu[k] + h;
-      }
+      for (int k = 0; k < K; ++k)
+        if (klo[k] <= x && khi[k] > reach) reach = khi[k];
       if (reach <= x) { ok = false; break; }
       x = reach;
     }
@@ -798,6 +824,11 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     for (int i = 0; i < 8; ++i) prof[role * 9 + i] = pc[i];
     prof[role * 9 + 8] = clock64() - t_start;
   }
+  if (prof && lane == 0 && (warp == kFirstEpiWarp || warp == 1)) {   // per CTA: epilogue / MMA role totals, phase B, accumulator wait
+    long long* pq = prof + 45 + (long long)blockIdx.x * 4;
+    if (warp == 1) pq[3] = clock64() - t_start;
+    else { pq[0] = clock64() - t_start; pq[1] = pc[4]; pq[2] = pc[0]; }
+  }
 #endif
   tc_fence_before_sync();
   __syncthreads();
@@ -857,8 +888,8 @@ int tkl_window_ts_launch(TklParams& P, const DeviceInfo& dev, cudaStream_t strea
 #ifdef MMB200_ENABLE_PROF
   const bool do_prof = getenv("MMB200_TKL_TS_PROF") != nullptr;
   if (do_prof) {
-    MMB_CHECK_CUDA(cudaMalloc(&prof, 45 * sizeof(long long)));
-    MMB_CHECK_CUDA(cudaMemset(prof, 0, 45 * sizeof(long long)));
+    MMB_CHECK_CUDA(cudaMalloc(&prof, (45 + 4 * 160) * sizeof(long long)));
+    MMB_CHECK_CUDA(cudaMemset(prof, 0, (45 + 4 * 160) * sizeof(long long)));
   }
 #endif
   static bool attr_set[2][64] = {};
@@ -879,9 +910,22 @@ int tkl_window_ts_launch(TklParams& P, const DeviceInfo& dev, cudaStream_t strea
   MMB_CHECK_CUDA(cudaGetLastError());
 #ifdef MMB200_ENABLE_PROF
   if (do_prof) {
-    long long h[45];
+    long long h[45 + 4 * 160];
     MMB_CHECK_CUDA(cudaStreamSynchronize(stream));
     MMB_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost));
+    {
+      long long mx[4] = {0, 0, 0, 0}, sm[4] = {0, 0, 0, 0};
+      int arg = 0;
+      for (int x = 0; x < grid && x < 160; ++x)
+        for (int i = 0; i < 4; ++i) {
+          const long long v = h[45 + 4 * x + i];
+          sm[i] += v;
+          if (v > mx[i]) { mx[i] = v; if (i == 0) arg = x; }
+        }
+      fprintf(stderr, "tkl_ts_prof per CTA (max / mean): epilogue total %lld / %lld (slowest CTA %d: phaseB %lld wait_accfull %lld) | phaseB %lld / %lld | "
+              "wait_accfull %lld / %lld | mma role total %lld / %lld\n", mx[0], sm[0] / grid, arg, h[45 + 4 * arg + 1], h[45 + 4 * arg + 2], mx[1],
+              sm[1] / grid, mx[2], sm[2] / grid, mx[3], sm[3] / grid);
+    }
     MMB_CHECK_CUDA(cudaFree(prof));
     fprintf(stderr,
             "tkl_ts_prof cycles (CTA 0): tma total %lld wait_raw_empty %lld | mma total %lld wait_accempty %lld wait_op_full %lld | qconv total %lld "
