@@ -580,18 +580,21 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       for (int r = 0; r < kBlk; ++r) suf[r] = 0.f;
       int acc_slot = 0, nr = 0;
       uint32_t accphase = 0;
-      auto fetch_mask = [&](int bb, int tt, bool& pres, uint64_t& raw) {
-        pres = false;
-        raw = 0;
-        if (row < kTileRows) {
-          const int c = tt * kTileSlots + row / kChunk;
-          const int pk = c < P.C ? P.slot_to_packed[(int64_t)bb * P.C + c] : -1;
-          pres = pk >= 0;
-          if (pres) raw = dmt != MMB200_MASK_NONE ? mask_raw(P.chunk_mask, dmt, (int64_t)pk * kChunk + (row % kChunk)) : 1;
-        }
+      // This position's mask word needs two dependent global loads (slot map, then mask).  They are issued one and two
+      // tiles ahead -- the packed index of tile n + 2 and, with the index fetched a tile earlier, the mask word of tile
+      // n + 1 -- at the end of phase A, so each has a whole phase B to arrive.
+      auto fetch_slot = [&](int bb, int tt) -> int {
+        if (row >= kTileRows) return -1;
+        const int c = tt * kTileSlots + row / kChunk;
+        return c < P.C ? P.slot_to_packed[(int64_t)bb * P.C + c] : -1;
       };
-      bool have_next = false, nxt_present = false;
-      uint64_t nxt_draw = 0;
+      auto fetch_word = [&](int pk) -> uint64_t {
+        if (pk < 0) return 0;
+        return dmt != MMB200_MASK_NONE ? mask_raw(P.chunk_mask, dmt, (int64_t)pk * kChunk + (row % kChunk)) : 1;
+      };
+      int have_ahead = 0;          // how many of the following tiles have their prefetches in flight (0, 1 or 2)
+      int pk_n1 = -1, pk_n2 = -1;  // packed chunk index of this position in tiles n + 1, n + 2
+      uint64_t draw_n1 = 0;
       int cur_doc = -1;
       int n_doc_warps = 0;   // epilogue warps holding an unmasked query row of the current document
       float qm_i = 0.f;
@@ -660,9 +663,16 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         // ---- phase A: accumulator -> cosine tile -------------------------------------------------------------
         // this position's mask word was fetched while the previous tile was in phase B (two dependent global loads --
         // slot map, then mask -- that the accumulator wait no longer hides: the producers run ahead of the epilogue)
-        if (!have_next) fetch_mask(b, t, nxt_present, nxt_draw);
-        const uint64_t draw = nxt_draw;
-        const bool present = nxt_present;
+        int pk_cur;
+        uint64_t draw;
+        if (have_ahead == 0) {   // first tile of the share: nothing was prefetched
+          pk_cur = fetch_slot(b, t);
+          draw = fetch_word(pk_cur);
+        } else {
+          pk_cur = pk_n1;
+          draw = draw_n1;
+        }
+        const bool present = pk_cur >= 0;
         TKL_MARK(7);   // bookkeeping between tiles, document switch
         mbar_wait<true>(&S->accfull[acc_slot], accphase);
         TKL_MARK(0);   // wait for the accumulator
@@ -695,11 +705,17 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         if (++acc_slot == kAcc) { acc_slot = 0; accphase ^= 1u; }
         if (++nr == kNormRing) nr = 0;
-        {   // mask word of this position in the NEXT tile: in flight during the token counts and phase B
+        {   // prefetches for the next two tiles (see fetch_slot above)
           TileWalk tn = tw;
           tn.next();
-          have_next = tn.valid();
-          if (have_next) fetch_mask(tn.b, tn.t, nxt_present, nxt_draw);
+          if (!tn.valid()) {
+            have_ahead = 0;
+          } else {
+            pk_n1 = have_ahead == 2 ? pk_n2 : fetch_slot(tn.b, tn.t);
+            draw_n1 = fetch_word(pk_n1);   // waits for pk_n1 only on the first tile of a share
+            tn.next();
+            if (tn.valid()) { pk_n2 = fetch_slot(tn.b, tn.t); have_ahead = 2; } else { have_ahead = 1; }
+          }
         }
         TKL_MARK(1);   // phase A
         named_bar_sync(2, kEpiThreads);
@@ -809,8 +825,12 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         if (!tw.halo && et < kTilePairs) {
           const int w = t * kTilePairs - (kBlk - 1) + et;
           if (w >= 0 && w < P.W) {
+            float pv[kEpiWarps];
+#pragma unroll
+            for (int ww = 0; ww < kEpiWarps; ++ww) pv[ww] = ww < n_doc_warps ? S->part[ww][et] : 0.f;   // loads in flight together
             float s = 0.f;
-            for (int ww = 0; ww < n_doc_warps; ++ww) s += S->part[ww][et];
+#pragma unroll
+            for (int ww = 0; ww < kEpiWarps; ++ww) s += pv[ww];   // fixed order; the zeros of idle warps change nothing
             P.window_score[(int64_t)b * P.W + w] = s;
           }
         }
