@@ -349,7 +349,20 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
       for (int k = 0; k < KB; ++k) acc[k] = 0.f;
       uint64_t qraw = 0;
-      if (ew == 0 && lane < P.Lq) qraw = qmt != MMB200_MASK_NONE ? mask_raw(P.q_mask, qmt, p * (int64_t)P.Lq + lane) : 1;
+      if (lane < P.Lq) qraw = qmt != MMB200_MASK_NONE ? mask_raw(P.q_mask, qmt, p * (int64_t)P.Lq + lane) : 1;
+      // Short queries: phase B has lane = query row, so a 6-token query would leave 26 lanes of every MUFU instruction
+      // idle.  With q_hi = 1 + last unmasked query row, the warp's lanes are dealt as 32 / qp sub-streams of qp query rows
+      // (qp = 4, 8, 16 or 32 >= q_hi); sub-stream s takes the document rows r + 16 s, and the sub-streams are added at
+      // the end of the pair.  Rows >= qp are masked query rows: their S is not needed (it is reported as 0).
+      int qp = 32;
+      if (qmt != MMB200_MASK_NONE) {
+        const unsigned qm_bits = __ballot_sync(0xffffffffu, lane < P.Lq && mask_test(qraw, qmt));
+        const int q_hi = qm_bits ? 32 - __clz(qm_bits) : 0;
+        qp = q_hi <= 4 ? 4 : q_hi <= 8 ? 8 : q_hi <= 16 ? 16 : 32;
+      }
+      const int qi = lane & (qp - 1);            // query row of this lane in phase B
+      const int sub16 = 16 * (lane / qp);        // document-row offset of this lane's sub-stream
+      const int rstep = 16 * (32 / qp);          // document rows one warp iteration advances by
       for (int t = 0; t < tiles; ++t, ++tile_seq) {
         const int row = qd * 32 + lane;          // document row inside the tile
         const int g = t * 128 + row;
@@ -398,14 +411,15 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           const int* lv = S->live[tile_seq & 1];
           const int rows_live = max(max(lv[0], lv[1]), max(lv[2], lv[3]));
           auto cos_at = [&](int r) -> float {
-            return r < rows_live ? cbuf[r * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)] : kSentinel;
+            return r < rows_live ? cbuf[r * 32 + (((qi >> 2) ^ (r & 7)) << 2) + (qi & 3)] : kSentinel;
           };
           const float* lgs = S->lg[tile_seq & 1];
-          float c0 = cos_at(ew), c1 = cos_at(ew + 8);
-          float l0 = lgs[ew], l1 = lgs[ew + 8];
-          for (int r = ew; r < rows_live; r += 16) {
-            const float n0 = cos_at(r + 16), n1 = cos_at(r + 24);
-            const float m0 = lgs[(r + 16) & 127], m1 = lgs[(r + 24) & 127];
+          float c0 = cos_at(ew + sub16), c1 = cos_at(ew + sub16 + 8);
+          float l0 = lgs[(ew + sub16) & 127], l1 = lgs[(ew + sub16 + 8) & 127];
+          for (int r0 = ew; r0 < rows_live; r0 += rstep) {   // uniform trip count: rows past rows_live read the sentinel
+            const int r = r0 + sub16 + rstep;
+            const float n0 = cos_at(r), n1 = cos_at(r + 8);
+            const float m0 = lgs[r & 127], m1 = lgs[(r + 8) & 127];
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
               const float m = kRegConst ? mu_r[k] : S->mu[k], a = kRegConst ? a_r[k] : S->a[k];
@@ -420,9 +434,17 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
       // ---- end of pair: S_ik = sum over the 8 warps, log, mask, per-kernel sums, score ----
       named_bar_sync(5, kEpiThreads);  // every warp is done reading the cosine tiles that spart aliases
+      if (qp < 32) {   // warp-uniform: add the sub-streams; afterwards every lane holds the total of its query row
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+          float v = acc[k];
+          for (int o = qp; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          acc[k] = lane < qp ? v : 0.f;
+        }
+      }
 #pragma unroll
       for (int k = 0; k < KB; ++k) spart[(ew * KB + k) * 32 + lane] = acc[k];
-      if (ew == 0) S->qm[lane] = (lane < P.Lq && mask_test(qraw, qmt)) ? 1.f : 0.f;
+      if (ew == 0) S->qm[lane] = (lane < P.Lq && mask_test(qraw, qmt)) ? 1.f : 0.f;   // qraw = 0 for lanes >= Lq
       named_bar_sync(2, kEpiThreads);
       {
         const bool q_live = S->qm[lane] != 0.f;
