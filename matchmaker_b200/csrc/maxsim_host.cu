@@ -21,34 +21,45 @@ template <>
 __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
 // Backward of score[p] = sum_i max_j <q_i, d_j> (autograd of matchmaker/models/colbert.py:68-75):
-//   grad_q[qi][i]   += g[p] * d[di][j*(i)]
-//   grad_d[di][j*]  += g[p] * q[qi][i]
-// One CTA per pair; thread k owns embedding element k (strided); query tokens are visited
-// sequentially so the adds into this pair's private document gradient are race-free and
-// deterministic.  grad_q is shared by the docs_per_query pairs of one query -> atomics there.
+//   grad_q[qi][i]   = sum over the pairs p of query qi of  g[p] * d[p][j*(p, i)]
+//   grad_d[p][j*]  += g[p] * q[qi][i]
+// Two kernels, no atomics, every sum in a fixed order (round 1 added the docs_per_query contributions to grad_q with
+// atomicAdd: run-to-run different low bits):
+//   maxsim_bwd_d_kernel  one CTA per pair; thread k owns embedding element k (strided); query tokens are visited
+//                        sequentially, so the adds into this pair's private document gradient are race-free and ordered
+//   maxsim_bwd_q_kernel  one CTA per (query, token): walks the query's docs_per_query pairs in order
 template <typename T>
-__global__ void __launch_bounds__(128) maxsim_bwd_kernel(const T* __restrict__ q, const T* __restrict__ d,
-                                                         const float* __restrict__ grad_out,
-                                                         const int32_t* __restrict__ argmax, float* grad_q,
-                                                         float* grad_d, int64_t n_pairs, int docs_per_query,
-                                                         int Lq, int Ld, int dim) {
+__global__ void __launch_bounds__(128) maxsim_bwd_d_kernel(const T* __restrict__ q, const float* __restrict__ grad_out,
+                                                           const int32_t* __restrict__ argmax, float* grad_d, int64_t n_pairs,
+                                                           int docs_per_query, int Lq, int Ld, int dim) {
   for (int64_t p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-    const int64_t qi = p / docs_per_query, di = p;
+    const int64_t qi = p / docs_per_query;
     const float g = grad_out[p];
     const T* qp = q + qi * (int64_t)Lq * dim;
-    const T* dp = d + di * (int64_t)Ld * dim;
-    float* gq = grad_q + qi * (int64_t)Lq * dim;
-    float* gd = grad_d + di * (int64_t)Ld * dim;
+    float* gd = grad_d + p * (int64_t)Ld * dim;
     for (int i = 0; i < Lq; ++i) {
       const int a = argmax[p * Lq + i];
       if (a < 0) continue;  // uniform across the CTA
-      for (int k = threadIdx.x; k < dim; k += blockDim.x) {
-        const float qv = ld_as_float(qp + (int64_t)i * dim + k);
-        const float dv = ld_as_float(dp + (int64_t)a * dim + k);
-        gd[(int64_t)a * dim + k] += g * qv;
-        if (docs_per_query == 1) gq[(int64_t)i * dim + k] = g * dv;
-        else atomicAdd(gq + (int64_t)i * dim + k, g * dv);
+      for (int k = threadIdx.x; k < dim; k += blockDim.x) gd[(int64_t)a * dim + k] += g * ld_as_float(qp + (int64_t)i * dim + k);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) maxsim_bwd_q_kernel(const T* __restrict__ d, const float* __restrict__ grad_out,
+                                                           const int32_t* __restrict__ argmax, float* grad_q, int64_t n_q,
+                                                           int64_t n_pairs, int docs_per_query, int Lq, int Ld, int dim) {
+  for (int64_t item = blockIdx.x; item < n_q * Lq; item += gridDim.x) {
+    const int64_t qi = item / Lq;
+    const int i = (int)(item % Lq);
+    const int64_t p0 = qi * docs_per_query, p1 = min(n_pairs, p0 + docs_per_query);
+    for (int k = threadIdx.x; k < dim; k += blockDim.x) {
+      float acc = 0.f;
+      for (int64_t p = p0; p < p1; ++p) {
+        const int a = argmax[p * Lq + i];
+        if (a >= 0) acc = fmaf(grad_out[p], ld_as_float(d + (p * Ld + a) * (int64_t)dim + k), acc);
       }
+      grad_q[(qi * Lq + i) * (int64_t)dim + k] = acc;
     }
   }
 }
@@ -119,20 +130,23 @@ extern "C" int mmb200_maxsim_bwd(const void* q, const void* d, const float* grad
     return MMB200_ERR_UNSUPPORTED;
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  MMB_CHECK_CUDA(cudaMemsetAsync(grad_q, 0, (size_t)n_q * Lq * dim * sizeof(float), stream));
   MMB_CHECK_CUDA(cudaMemsetAsync(grad_d, 0, (size_t)n_d * Ld * dim * sizeof(float), stream));
-  if (n_pairs == 0) return MMB200_OK;
-  const int grid = (int)std::min<int64_t>((int64_t)dev.sm_count * 16, n_pairs);
-  if (dtype == MMB200_F16)
-    maxsim_bwd_kernel<__half><<<grid, 128, 0, stream>>>((const __half*)q, (const __half*)d, grad_out, argmax, grad_q,
-                                                        grad_d, n_pairs, docs_per_query, Lq, Ld, dim);
-  else if (dtype == MMB200_BF16)
-    maxsim_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)d,
-                                                               grad_out, argmax, grad_q, grad_d, n_pairs,
-                                                               docs_per_query, Lq, Ld, dim);
-  else
-    maxsim_bwd_kernel<float><<<grid, 128, 0, stream>>>((const float*)q, (const float*)d, grad_out, argmax, grad_q,
-                                                       grad_d, n_pairs, docs_per_query, Lq, Ld, dim);
+  if (n_pairs == 0) {
+    MMB_CHECK_CUDA(cudaMemsetAsync(grad_q, 0, (size_t)n_q * Lq * dim * sizeof(float), stream));
+    return MMB200_OK;
+  }
+  const int grid_d = (int)std::min<int64_t>((int64_t)dev.sm_count * 16, n_pairs);
+  const int grid_q = (int)std::min<int64_t>((int64_t)dev.sm_count * 16, n_q * Lq);
+#define MMB_LAUNCH_BWD(T)                                                                                                       \
+  do {                                                                                                                          \
+    maxsim_bwd_d_kernel<T><<<grid_d, 128, 0, stream>>>((const T*)q, grad_out, argmax, grad_d, n_pairs, docs_per_query, Lq, Ld, dim); \
+    maxsim_bwd_q_kernel<T><<<grid_q, 128, 0, stream>>>((const T*)d, grad_out, argmax, grad_q, n_q, n_pairs, docs_per_query, Lq, Ld, \
+                                                       dim);                                                                    \
+  } while (0)
+  if (dtype == MMB200_F16) MMB_LAUNCH_BWD(__half);
+  else if (dtype == MMB200_BF16) MMB_LAUNCH_BWD(__nv_bfloat16);
+  else MMB_LAUNCH_BWD(float);
+#undef MMB_LAUNCH_BWD
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;
 }

@@ -131,6 +131,31 @@ def test_argmax_and_backward_vs_autograd():
     assert_close_rel(cd.grad, dr.grad, what="grad_d")
 
 
+def test_backward_is_deterministic_with_many_docs_per_query():
+    """grad_q sums the contributions of a query's docs_per_query pairs: a fixed order (no atomics), so two runs agree
+    bit for bit; fp16 inputs take the tcgen05 forward with argmax."""
+    from matchmaker_b200 import autograd
+    q, d, qm, dm = O.synth_colbert_inputs(5, 300, 32, 180, 128, seed=77, full_q=False)
+    g = torch.randn(5 * 300, generator=torch.Generator().manual_seed(2)).to(DEV)
+    grads = []
+    for _ in range(3):
+        cq = q.to(DEV).requires_grad_(True)
+        cd = d.to(DEV).requires_grad_(True)
+        out = autograd.maxsim(cq, cd, qm.to(DEV), dm.to(DEV), docs_per_query=300)
+        out.backward(g)
+        grads.append((cq.grad.clone(), cd.grad.clone()))
+    assert all(torch.equal(grads[0][0], x[0]) and torch.equal(grads[0][1], x[1]) for x in grads[1:])
+    # against torch autograd on the upcast values
+    qr = q.float().clone().requires_grad_(True)
+    dr = d.float().clone().requires_grad_(True)
+    s = torch.bmm(qr.repeat_interleave(300, dim=0), dr.transpose(2, 1))
+    s = s.masked_fill(~dm.bool().unsqueeze(1), -1000.0).max(-1).values
+    s = (s * qm.repeat_interleave(300, dim=0).float()).sum(-1)
+    s.backward(g.cpu())
+    assert_close_rel(grads[0][0].float(), qr.grad, rel=2e-3, what="grad_q")
+    assert_close_rel(grads[0][1].float(), dr.grad, rel=2e-3, what="grad_d")
+
+
 def test_baseline_size_properties():
     """BASELINE config 3 (64 queries x 1000 docs, Lq=32, Ld=180, dim=128, fp16): size-independent properties
     -- tcgen05 == SIMT, permutation equivariance over documents, chunking invariance, oracle on a sample."""
