@@ -35,18 +35,27 @@ def maxsim(q: torch.Tensor, d: torch.Tensor, q_mask: Optional[torch.Tensor] = No
     return _MaxSim.apply(q, d, q_mask, d_mask, docs_per_query)
 
 
+# "auto": forward that saves its cosines + tcgen05 backward where the shape allows; "simt": always the FFMA backward
+KP_TRAIN_IMPL = "auto"
+
+
 class _KernelPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale, doc_gate, clamp_min, bias):
         # needs_input_grad (not tensor.requires_grad: parameters always require grad, also under no_grad)
         need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 6, 7, 9))
+        # training step on the tensor cores when the shape allows it (KP_TRAIN_IMPL = "simt" keeps the FFMA backward)
+        tc = (need_grad and doc_gate is None and KP_TRAIN_IMPL != "simt"
+              and interaction.kernel_pool_train_supported(q.shape[1], d.shape[1], q.shape[2], mu.numel()))
         out = interaction.kernel_pool(q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale,
                                       want_per_kernel=True, want_per_kernel_query=need_grad, doc_gate=doc_gate,
-                                      clamp_min=clamp_min, bias=bias)
+                                      clamp_min=clamp_min, bias=bias, save_for_backward=tc)
         if need_grad:
             empty = torch.empty(0, device=q.device)
             ctx.save_for_backward(q, d, q_mask, d_mask, mu, sigma, weight, alpha if alpha is not None else empty,
-                                  out["per_kernel_query"], doc_gate if doc_gate is not None else empty)
+                                  out["per_kernel_query"], doc_gate if doc_gate is not None else empty,
+                                  out["saved"] if tc else empty)
+            ctx.tc = tc
             ctx.has_alpha, ctx.has_gate = alpha is not None, doc_gate is not None
             ctx.log_scale, ctx.clamp_min = log_scale, clamp_min
         ctx.mark_non_differentiable(out["per_kernel"])
@@ -54,11 +63,11 @@ class _KernelPool(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_score, _grad_pk):
-        q, d, q_mask, d_mask, mu, sigma, weight, alpha, S, gate = ctx.saved_tensors
+        q, d, q_mask, d_mask, mu, sigma, weight, alpha, S, gate, saved = ctx.saved_tensors
         alpha = alpha if ctx.has_alpha else None
         gate = gate if ctx.has_gate else None
         res = interaction.kernel_pool_bwd(q, d, q_mask, d_mask, mu, sigma, weight, alpha, S, grad_score, ctx.log_scale,
-                                          doc_gate=gate, clamp_min=ctx.clamp_min)
+                                          doc_gate=gate, clamp_min=ctx.clamp_min, saved=saved if ctx.tc else None)
         gq, gd, ga, gw = res[:4]
         gg = res[4].view_as(gate) if gate is not None else None
         gw = gw.view_as(weight)

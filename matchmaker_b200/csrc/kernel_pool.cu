@@ -422,20 +422,31 @@ __global__ void __launch_bounds__(kKpThreads) kernel_pool_bwd_simt(KpParams P) {
   }
 }
 
-// grad_weight[k] = sum_b ws_weight[b,k]; grad_alpha likewise.  One block, fixed order -> deterministic.
-__global__ void kp_reduce_batch(const float* __restrict__ ws_w, const float* __restrict__ ws_a, float* gw, float* ga,
-                                int64_t B, int K) {
-  __shared__ float part[2][8][32];
-  const int k = threadIdx.x & 31, g = threadIdx.x >> 5;
-  float sw = 0.f, sa = 0.f;
-  if (k < K)
-    for (int64_t b = g; b < B; b += 8) { sw += ws_w[b * K + k]; sa += ws_a[b * K + k]; }
-  part[0][g][k] = sw;
-  part[1][g][k] = sa;
+// grad_weight[k] = sum_b ws_weight[b,k]; grad_alpha likewise.  One block per kernel k, fixed summation order ->
+// deterministic.  (One block for everything walked the batch with 128 dependent loads per thread: 40 us at B = 1024,
+// a fifth of the tensor-core backward.)
+__global__ void __launch_bounds__(256) kp_reduce_batch(const float* __restrict__ ws_w, const float* __restrict__ ws_a, float* gw,
+                                                        float* ga, int64_t B, int K) {
+  __shared__ float part[2][8];
+  const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  float sw[4] = {0.f, 0.f, 0.f, 0.f}, sa[4] = {0.f, 0.f, 0.f, 0.f};
+  int64_t b = t;
+  for (; b + 768 < B; b += 1024) {   // four independent loads in flight per thread
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { sw[u] += ws_w[(b + 256 * u) * K + k]; sa[u] += ws_a[(b + 256 * u) * K + k]; }
+  }
+  for (; b < B; b += 256) { sw[0] += ws_w[b * K + k]; sa[0] += ws_a[b * K + k]; }
+  float vw = (sw[0] + sw[1]) + (sw[2] + sw[3]), va = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vw += __shfl_xor_sync(0xffffffffu, vw, o);
+    va += __shfl_xor_sync(0xffffffffu, va, o);
+  }
+  if (lane == 0) { part[0][warp] = vw; part[1][warp] = va; }
   __syncthreads();
-  if (g == 0 && k < K) {
+  if (t == 0) {
     float a = 0.f, c = 0.f;
-    for (int x = 0; x < 8; ++x) { a += part[0][x][k]; c += part[1][x][k]; }
+    for (int x = 0; x < 8; ++x) { a += part[0][x]; c += part[1][x]; }
     if (gw) gw[k] = a;
     if (ga) ga[k] = c;
   }
@@ -496,15 +507,81 @@ extern "C" int mmb200_kernel_pool_fwd(const float* q, const float* d, const void
                                    per_kernel_query, cosine, B, Lq, Ld, D, K, log_scale, 1e-10f, 0.f, mask_dtype, impl, stream_);
 }
 
+namespace mmb {
+// the envelope of the tcgen05 training pair (forward that saves its cosines + backward that consumes them)
+static bool kp_train_tc_shape_ok(int Lq, int Ld, int D, int K) {
+  return Lq >= 1 && Lq <= 32 && Ld >= 1 && K >= 1 && K <= 32 && D >= 4 && D % 4 == 0 && D <= 320;
+}
+static int kp_fwd_impl(const float* q, const float* d, const void* q_mask, const void* d_mask, const float* doc_gate,
+                       const float* mu, const float* sigma, const float* alpha, const float* weight, float* score,
+                       float* per_kernel, float* per_kernel_query, float* cosine, float* saved, int64_t B, int32_t Lq,
+                       int32_t Ld, int32_t D, int32_t K, float log_scale, float clamp_min, float score_bias,
+                       int32_t mask_dtype, int32_t impl, void* stream_);
+static int kp_bwd_impl(const float* q, const float* d, const void* q_mask, const void* d_mask, const float* doc_gate,
+                       const float* mu, const float* sigma, const float* alpha, const float* weight,
+                       const float* per_kernel_query, const float* saved, const float* grad_score, float* grad_q,
+                       float* grad_d, float* grad_gate, float* grad_alpha, float* grad_weight, float* workspace, int64_t B,
+                       int32_t Lq, int32_t Ld, int32_t D, int32_t K, float log_scale, float clamp_min, int32_t mask_dtype,
+                       void* stream_);
+}  // namespace mmb
+
 extern "C" int mmb200_kernel_pool_fwd_ex(const float* q, const float* d, const void* q_mask, const void* d_mask,
                                          const float* doc_gate, const float* mu, const float* sigma, const float* alpha,
                                          const float* weight, float* score, float* per_kernel, float* per_kernel_query,
                                          float* cosine, int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K,
                                          float log_scale, float clamp_min, float score_bias, int32_t mask_dtype,
                                          int32_t impl, void* stream_) {
+  return mmb::kp_fwd_impl(q, d, q_mask, d_mask, doc_gate, mu, sigma, alpha, weight, score, per_kernel, per_kernel_query,
+                          cosine, nullptr, B, Lq, Ld, D, K, log_scale, clamp_min, score_bias, mask_dtype, impl, stream_);
+}
+
+extern "C" int32_t mmb200_kernel_pool_train_tc_supported(int32_t Lq, int32_t Ld, int32_t D, int32_t K) {
+  return mmb::kp_train_tc_shape_ok(Lq, Ld, D, K) ? 1 : 0;
+}
+
+extern "C" int64_t mmb200_kernel_pool_saved_floats(int64_t B, int32_t Ld) { return mmb::kp_saved_floats(B, Ld); }
+
+extern "C" int mmb200_kernel_pool_fwd_train(const float* q, const float* d, const void* q_mask, const void* d_mask,
+                                            const float* mu, const float* sigma, const float* alpha, const float* weight,
+                                            float* score, float* per_kernel, float* per_kernel_query, float* saved,
+                                            int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K, float log_scale,
+                                            float clamp_min, float score_bias, int32_t mask_dtype, void* stream_) {
+  using namespace mmb;
+  MMB_REQUIRE(saved != nullptr && per_kernel_query != nullptr, "saved and per_kernel_query must be non-null");
+  if (!kp_train_tc_shape_ok(Lq, Ld, D, K)) {
+    set_error("kernel_pool_fwd_train: shape outside the tcgen05 training envelope (Lq <= 32, K <= 32, D % 4 == 0, D <= 320)");
+    return MMB200_ERR_UNSUPPORTED;
+  }
+  return kp_fwd_impl(q, d, q_mask, d_mask, nullptr, mu, sigma, alpha, weight, score, per_kernel, per_kernel_query, nullptr,
+                     saved, B, Lq, Ld, D, K, log_scale, clamp_min, score_bias, mask_dtype, MMB200_IMPL_TCGEN05, stream_);
+}
+
+extern "C" int mmb200_kernel_pool_bwd_saved(const float* q, const float* d, const void* q_mask, const void* d_mask,
+                                            const float* mu, const float* sigma, const float* alpha, const float* weight,
+                                            const float* per_kernel_query, const float* saved, const float* grad_score,
+                                            float* grad_q, float* grad_d, float* grad_alpha, float* grad_weight,
+                                            float* workspace, int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K,
+                                            float log_scale, float clamp_min, int32_t mask_dtype, void* stream_) {
+  using namespace mmb;
+  MMB_REQUIRE(saved != nullptr, "saved must be non-null");
+  if (!kp_train_tc_shape_ok(Lq, Ld, D, K)) {
+    set_error("kernel_pool_bwd_saved: shape outside the tcgen05 training envelope (Lq <= 32, K <= 32, D % 4 == 0, D <= 320)");
+    return MMB200_ERR_UNSUPPORTED;
+  }
+  return kp_bwd_impl(q, d, q_mask, d_mask, nullptr, mu, sigma, alpha, weight, per_kernel_query, saved, grad_score, grad_q,
+                     grad_d, nullptr, grad_alpha, grad_weight, workspace, B, Lq, Ld, D, K, log_scale, clamp_min, mask_dtype,
+                     stream_);
+}
+
+static int mmb::kp_fwd_impl(const float* q, const float* d, const void* q_mask, const void* d_mask, const float* doc_gate,
+                            const float* mu, const float* sigma, const float* alpha, const float* weight, float* score,
+                            float* per_kernel, float* per_kernel_query, float* cosine, float* saved, int64_t B, int32_t Lq,
+                            int32_t Ld, int32_t D, int32_t K, float log_scale, float clamp_min, float score_bias,
+                            int32_t mask_dtype, int32_t impl, void* stream_) {
   using namespace mmb;
   MMB_REQUIRE(clamp_min > 0.f, "clamp_min must be positive");
   KpParams P{};
+  P.saved = saved;
   P.gate = doc_gate; P.clamp_min = clamp_min; P.bias = score_bias;
   P.q = q; P.d = d; P.q_mask = q_mask; P.d_mask = d_mask; P.mu = mu; P.sigma = sigma; P.alpha = alpha; P.weight = weight;
   P.B = B; P.Lq = Lq; P.Ld = Ld; P.D = D; P.K = K; P.mask_dtype = mask_dtype; P.log_scale = log_scale;
@@ -552,9 +629,28 @@ extern "C" int mmb200_kernel_pool_bwd_ex(const float* q, const float* d, const v
                                          float* grad_weight, float* workspace, int64_t B, int32_t Lq, int32_t Ld,
                                          int32_t D, int32_t K, float log_scale, float clamp_min, int32_t mask_dtype,
                                          void* stream_) {
+  return mmb::kp_bwd_impl(q, d, q_mask, d_mask, doc_gate, mu, sigma, alpha, weight, per_kernel_query, nullptr, grad_score,
+                          grad_q, grad_d, grad_gate, grad_alpha, grad_weight, workspace, B, Lq, Ld, D, K, log_scale, clamp_min,
+                          mask_dtype, stream_);
+}
+
+static int mmb::kp_bwd_impl(const float* q, const float* d, const void* q_mask, const void* d_mask, const float* doc_gate,
+                            const float* mu, const float* sigma, const float* alpha, const float* weight,
+                            const float* per_kernel_query, const float* saved, const float* grad_score, float* grad_q,
+                            float* grad_d, float* grad_gate, float* grad_alpha, float* grad_weight, float* workspace,
+                            int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K, float log_scale, float clamp_min,
+                            int32_t mask_dtype, void* stream_) {
   using namespace mmb;
   MMB_REQUIRE(clamp_min > 0.f, "clamp_min must be positive");
   KpParams P{};
+  P.saved = const_cast<float*>(saved);
+  // the tensor core drops the low 13 mantissa bits of the raw fp32 tiles: relative shrink 2^-10 u / m with u uniform in
+  // [0, 1) and the mantissa m log-uniform in [1, 2) -> mean 2^-11 / ln 2 * (1 - 1/2) = 0.72 * 2^-11 (measured on B200:
+  // -3.3e-4 without the factor, profiles/r02_kernel_pool_bwd_investigation.md)
+  P.tf32_comp = 1.0f + 0.72f / 2048.0f;
+#ifdef MMB200_ENABLE_PROF
+  if (const char* e = getenv("MMB200_KPB_COMP")) P.tf32_comp = (float)atof(e);
+#endif
   P.gate = doc_gate; P.clamp_min = clamp_min; P.grad_gate = grad_gate;
   P.q = q; P.d = d; P.q_mask = q_mask; P.d_mask = d_mask; P.mu = mu; P.sigma = sigma; P.alpha = alpha; P.weight = weight;
   P.B = B; P.Lq = Lq; P.Ld = Ld; P.D = D; P.K = K; P.mask_dtype = mask_dtype; P.log_scale = log_scale;
@@ -573,6 +669,18 @@ extern "C" int mmb200_kernel_pool_bwd_ex(const float* q, const float* d, const v
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc;
+  if (saved) {
+    bool handled = false;
+    rc = kernel_pool_bwd_tc(P, dev, stream, &handled);
+    if (!handled) {
+      if (rc == MMB200_OK) { set_error("kernel_pool_bwd_saved: arguments outside the tcgen05 backward's envelope"); rc = MMB200_ERR_UNSUPPORTED; }
+      return rc;
+    }
+    if (rc) return rc;
+    kp_reduce_batch<<<K, 256, 0, stream>>>(P.ws_weight, P.ws_alpha, grad_weight, grad_alpha, B, K);
+    MMB_CHECK_CUDA(cudaGetLastError());
+    return MMB200_OK;
+  }
   if (D <= 256) {
     if (K <= 12) rc = launch_bwd<12, 1>(P, dev, stream);
     else if (K <= 24) rc = launch_bwd<24, 1>(P, dev, stream);
@@ -583,7 +691,7 @@ extern "C" int mmb200_kernel_pool_bwd_ex(const float* q, const float* d, const v
     else rc = launch_bwd<32, 2>(P, dev, stream);
   }
   if (rc) return rc;
-  kp_reduce_batch<<<1, 256, 0, stream>>>(P.ws_weight, P.ws_alpha, grad_weight, grad_alpha, B, K);
+  kp_reduce_batch<<<K, 256, 0, stream>>>(P.ws_weight, P.ws_alpha, grad_weight, grad_alpha, B, K);
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;
 }

@@ -107,7 +107,7 @@ __device__ __forceinline__ void split4(const float4 v, uint32_t* hi, uint32_t* l
     }                                                         \
   } while (0)
 
-template <int KB, bool PROF>
+template <int KB, bool PROF, bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1)
 kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
                       const __grid_constant__ CUtensorMap tmap_d_last, KpParams P, int n_raw, int last_box_rows,
@@ -385,6 +385,22 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const float c = (__uint_as_float(rh[j]) + __uint_as_float(rl[j])) * rsd * S->rs_q[nr][16 * h + j];
             v[j] = valid ? c : kSentinel;
           }
+          if constexpr (SAVE) {  // training: leave the unmasked cosines and the norms for the tcgen05 backward
+            if (g < P.Ld) {
+              float* crow = P.saved + kp_saved_cos_off(p, P.Ld) + (int64_t)g * 32 + 16 * h;
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                float4 o;
+                o.x = (__uint_as_float(rh[4 * cc + 0]) + __uint_as_float(rl[4 * cc + 0])) * rsd * S->rs_q[nr][16 * h + 4 * cc + 0];
+                o.y = (__uint_as_float(rh[4 * cc + 1]) + __uint_as_float(rl[4 * cc + 1])) * rsd * S->rs_q[nr][16 * h + 4 * cc + 1];
+                o.z = (__uint_as_float(rh[4 * cc + 2]) + __uint_as_float(rl[4 * cc + 2])) * rsd * S->rs_q[nr][16 * h + 4 * cc + 2];
+                o.w = (__uint_as_float(rh[4 * cc + 3]) + __uint_as_float(rl[4 * cc + 3])) * rsd * S->rs_q[nr][16 * h + 4 * cc + 3];
+                *reinterpret_cast<float4*>(crow + 4 * cc) = o;
+              }
+              if (h == 0) P.saved[kp_saved_rsd_off(P.B, p, P.Ld) + g] = rsd;
+            }
+            if (t == 0 && ew == 0) P.saved[kp_saved_rsq_off(P.B, p, P.Ld) + lane] = S->rs_q[nr][lane];
+          }
           if (h == 0) {  // last live row of this quarter: phase B stops there instead of testing every row
             const uint32_t live = __ballot_sync(0xffffffffu, valid);
             if (lane == 0) S->live[tile_seq & 1][qd] = live ? qd * 32 + 32 - __clz(live) : 0;
@@ -507,8 +523,8 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
     long long h[13] = {0};
     MMB_CHECK_CUDA(cudaMalloc(&prof, sizeof(h)));
     MMB_CHECK_CUDA(cudaMemset(prof, 0, sizeof(h)));
-    MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_ts_kernel<21, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel_pool_ts_kernel<21, true><<<grid, kThreads, smem, stream>>>(tq, td, td_last, P, n_raw, last_box_rows, prof);
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_ts_kernel<21, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel_pool_ts_kernel<21, true, false><<<grid, kThreads, smem, stream>>>(tq, td, td_last, P, n_raw, last_box_rows, prof);
     MMB_CHECK_CUDA(cudaStreamSynchronize(stream));
     MMB_CHECK_CUDA(cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost));
     MMB_CHECK_CUDA(cudaFree(prof));
@@ -519,8 +535,13 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
     return MMB200_OK;
   }
 #endif
-  MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_ts_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kernel_pool_ts_kernel<KB, false><<<grid, kThreads, smem, stream>>>(tq, td, td_last, P, n_raw, last_box_rows, nullptr);
+  if (P.saved) {
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_ts_kernel<KB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel_pool_ts_kernel<KB, false, true><<<grid, kThreads, smem, stream>>>(tq, td, td_last, P, n_raw, last_box_rows, nullptr);
+  } else {
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_ts_kernel<KB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel_pool_ts_kernel<KB, false, false><<<grid, kThreads, smem, stream>>>(tq, td, td_last, P, n_raw, last_box_rows, nullptr);
+  }
   MMB_CHECK_CUDA(cudaGetLastError());
   return MMB200_OK;
 }

@@ -152,6 +152,24 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* smem_d
       : "memory");
 }
 
+// shared memory -> global through a tensor map (bulk async-group completion).  The generic-proxy writes that
+// filled the box must be ordered before it with fence.proxy.async + a barrier.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most kPending of this thread's bulk groups still READ their shared-memory source afterwards
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation
 // ---------------------------------------------------------------------------------------------
@@ -194,6 +212,30 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+
+// MN-major fp32 / tf32 operand (the contraction index K runs over the ROWS of the stored tile, the M / N index is
+// contiguous): what a TMA box [K rows][32 fp32] is when the MMA reduces over its rows.  For 32-bit elements the tensor
+// core accepts exactly one shared-memory layout here, "128-byte swizzle with 32-byte atomicity" (descriptor layout type
+// 1; the TMA side is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 bytes whose four 32-byte units are XORed with
+// (row & 3).  Canonical form: atom = 4 K-rows x 128 bytes; the next 32 M/N elements sit lbo_bytes further (the next
+// box), the next 4 K-rows sbo_bytes = 512 further.  A kind::tf32 instruction (K = 8) consumes two 4-row groups: the
+// K-step advances the start address by 1024 bytes.  (With the ordinary 16-byte-atom SWIZZLE_128B the instruction
+// executes and writes zeros.)
+__device__ __forceinline__ uint64_t make_sw128x32_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes = 512) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;
+  return d;
+}
+// byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a [rows][128 B] tile in that layout
+__device__ __forceinline__ uint32_t sw128x32_offset(int row, int chunk) {
+  return (uint32_t)(row * 128 + ((((chunk >> 1) ^ row) & 3) << 5) + ((chunk & 1) << 4));
+}
+constexpr uint32_t kIdescBMajorMN = 1u << 16;   // instruction-descriptor bit: B operand is MN-major
+constexpr uint32_t kIdescAMajorMN = 1u << 15;
 
 enum : uint32_t { kFmtF16 = 0, kFmtBF16 = 1, kFmtTF32 = 2 };
 
@@ -293,6 +335,19 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// fp32 -> tf32, round to nearest (the tensor core itself drops the low 13 bits)
+__device__ __forceinline__ uint32_t f32_to_tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
 }
 
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -188,7 +188,7 @@ def kernel_pool(q: torch.Tensor, d: torch.Tensor, q_mask: torch.Tensor, d_mask: 
                 mu: torch.Tensor, sigma: torch.Tensor, weight: torch.Tensor, alpha: Optional[torch.Tensor] = None,
                 log_scale: float = 1.0, want_per_kernel: bool = False, want_per_kernel_query: bool = False,
                 want_cosine: bool = False, impl: str = "auto", doc_gate: Optional[torch.Tensor] = None,
-                clamp_min: float = 1e-10, bias: float = 0.0):
+                clamp_min: float = 1e-10, bias: float = 0.0, save_for_backward: bool = False):
     """Cosine match matrix + RBF kernel pooling, forward (knrm.py:52-84 / ecai20_tk.py:105-124).
 
     q [B,Lq,D], d [B,Ld,D] fp32; masks [B,L]; mu/sigma/weight(/alpha) [K].  Returns a dict with "score"
@@ -196,7 +196,11 @@ def kernel_pool(q: torch.Tensor, d: torch.Tensor, q_mask: torch.Tensor, d_mask: 
 
     Variants: ``doc_gate`` [B,Ld] multiplies every activation of its document term (TK-Sparse,
     cikm20_tk_sparse.py:135); ``clamp_min`` / ``bias`` are the 1e-4 floor and the Linear bias of IDCM's ESM scorer
-    (sigir21_idcm.py:185-186)."""
+    (sigir21_idcm.py:185-186).
+
+    ``save_for_backward=True`` (shapes for which :func:`kernel_pool_train_supported` holds, no ``doc_gate``) runs the
+    training forward: the result additionally carries "saved", the opaque state the tensor-core backward consumes
+    (:func:`kernel_pool_bwd` with ``saved=``), and "per_kernel_query"."""
     dev = _require_cuda(q, d, q_mask, d_mask, mu, sigma, weight, alpha, doc_gate)
     if q.dtype != torch.float32 or d.dtype != torch.float32:
         q, d = q.float(), d.float()  # the reference runs TK/KNRM with use_fp16: False (tk.yaml:6)
@@ -217,6 +221,19 @@ def kernel_pool(q: torch.Tensor, d: torch.Tensor, q_mask: torch.Tensor, d_mask: 
     if doc_gate is not None:
         gate = _f32c(doc_gate).reshape(B, Ld)
     lib = _lib.load()
+    if save_for_backward:
+        if gate is not None or want_cosine or not kernel_pool_train_supported(Lq, Ld, D, K):
+            raise _lib.MatchmakerB200Error("kernel_pool(save_for_backward=True): outside the tensor-core training envelope")
+        if pkq is None:
+            pkq = torch.empty((B, Lq, K), dtype=torch.float32, device=dev)
+        saved = torch.empty(int(lib.mmb200_kernel_pool_saved_floats(B, Ld)), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.mmb200_kernel_pool_fwd_train(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(mu), _ptr(sigma),
+                                                  _ptr(alpha), _ptr(weight), _ptr(score), _ptr(pk), _ptr(pkq), _ptr(saved),
+                                                  B, Lq, Ld, D, K, float(log_scale), float(clamp_min), float(bias), mcode,
+                                                  _stream(dev))
+        _lib.check(rc, "mmb200_kernel_pool_fwd_train")
+        return {"score": score, "per_kernel": pk, "per_kernel_query": pkq, "cosine": None, "saved": saved}
     with torch.cuda.device(dev):
         rc = lib.mmb200_kernel_pool_fwd_ex(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(gate), _ptr(mu), _ptr(sigma),
                                            _ptr(alpha), _ptr(weight), _ptr(score), _ptr(pk), _ptr(pkq), _ptr(cos),
@@ -226,10 +243,17 @@ def kernel_pool(q: torch.Tensor, d: torch.Tensor, q_mask: torch.Tensor, d_mask: 
     return {"score": score, "per_kernel": pk, "per_kernel_query": pkq, "cosine": cos}
 
 
+def kernel_pool_train_supported(Lq: int, Ld: int, D: int, K: int) -> bool:
+    """True when the tensor-core training pair (forward that saves its cosines + tcgen05 backward) covers the shape."""
+    return bool(_lib.load().mmb200_kernel_pool_train_tc_supported(int(Lq), int(Ld), int(D), int(K)))
+
+
 def kernel_pool_bwd(q, d, q_mask, d_mask, mu, sigma, weight, alpha, per_kernel_query, grad_score,
-                    log_scale: float = 1.0, doc_gate: Optional[torch.Tensor] = None, clamp_min: float = 1e-10):
+                    log_scale: float = 1.0, doc_gate: Optional[torch.Tensor] = None, clamp_min: float = 1e-10,
+                    saved: Optional[torch.Tensor] = None):
     """Backward of :func:`kernel_pool`: returns (grad_q, grad_d, grad_alpha or None, grad_weight[, grad_gate when a
-    ``doc_gate`` was given])."""
+    ``doc_gate`` was given]).  With ``saved`` (from ``kernel_pool(save_for_backward=True)``) both contractions run on the
+    tensor cores (tf32 operands: gradients within a few 1e-4 relative of the fp32 expression)."""
     dev = _require_cuda(q, d, per_kernel_query, grad_score)
     q, d = q.float().contiguous(), d.float().contiguous()
     B, Lq, D = q.shape
@@ -246,6 +270,17 @@ def kernel_pool_bwd(q, d, q_mask, d_mask, mu, sigma, weight, alpha, per_kernel_q
     gate = None if doc_gate is None else _f32c(doc_gate).reshape(B, Ld)
     gg = None if doc_gate is None else torch.empty((B, Ld), dtype=torch.float32, device=dev)
     lib = _lib.load()
+    if saved is not None:
+        if doc_gate is not None:
+            raise _lib.MatchmakerB200Error("kernel_pool_bwd(saved=...): doc_gate is not supported by the tensor-core backward")
+        with torch.cuda.device(dev):
+            rc = lib.mmb200_kernel_pool_bwd_saved(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(mu), _ptr(sigma),
+                                                  _ptr(alpha_c), _ptr(weight), _ptr(per_kernel_query.contiguous()),
+                                                  _ptr(saved), _ptr(_f32c(grad_score)), _ptr(gq), _ptr(gd), _ptr(ga),
+                                                  _ptr(gw), _ptr(ws), B, Lq, Ld, D, K, float(log_scale), float(clamp_min),
+                                                  mcode, _stream(dev))
+        _lib.check(rc, "mmb200_kernel_pool_bwd_saved")
+        return gq, gd, (ga if alpha is not None else None), gw
     with torch.cuda.device(dev):
         rc = lib.mmb200_kernel_pool_bwd_ex(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(gate), _ptr(mu), _ptr(sigma),
                                            _ptr(alpha_c), _ptr(weight), _ptr(per_kernel_query.contiguous()),

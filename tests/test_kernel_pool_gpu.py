@@ -265,3 +265,95 @@ def test_tcgen05_run_to_run_determinism():
     for _ in range(10):
         o = interaction.kernel_pool(*args, alpha=alpha.to(DEV), want_per_kernel_query=True, impl="tcgen05")
         assert torch.equal(o["score"], base["score"]) and torch.equal(o["per_kernel_query"], base["per_kernel_query"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training pair on the tensor cores: forward that saves its cosines + tcgen05 backward (kernel_pool_bwd_tc.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def _grad_close(a, b, what, rel=1e-3):
+    """1e-3 of the largest entry of the tensor (elementwise tiny entries are cancellation noise), the bar of the FFMA
+    backward's test above; the tf32 operands of the tensor-core backward sit at 1-3e-4."""
+    a, b = a.double().cpu(), b.double().cpu()
+    scale = b.abs().max().item()
+    err = (a - b).abs().max().item()
+    assert err <= rel * scale + 1e-12, f"{what}: max err {err:.3e} vs scale {scale:.3e} ({err / max(scale, 1e-300):.2e})"
+    return err / max(scale, 1e-300)
+
+
+TRAIN_SHAPES = [  # B, Lq, Ld, D, K-kind
+    (5, 30, 200, 300, "tk21"),      # BASELINE config 2 shape: two document tiles (128 + 72), ten feature boxes
+    (7, 30, 180, 300, "knrm11"),    # config 1 shape, exact-match kernel
+    (4, 32, 128, 64, "tk11"),       # one full tile
+    (3, 9, 129, 96, "tk11"),        # 128 + 1 rows; three feature boxes: a stage with a single box
+    (400, 8, 20, 32, "tk11"),       # more pairs than CTAs: every CTA walks several pairs through the double buffers
+    (6, 30, 300, 100, "tk21"),      # three tiles: the G groups alternate within and across pairs
+    (2, 2, 3, 4, "tk11"),           # smallest embedding (one 16-byte row)
+    (3, 30, 40, 320, "k32"),        # widest supported embedding, padded kernel count
+]
+
+
+@pytest.mark.parametrize("shape", TRAIN_SHAPES)
+def test_train_pair_tcgen05_vs_fp64(shape):
+    B, Lq, Ld, D, kind = shape
+    mu, sg, ls, _ = _kernels(kind)
+    mu, sg = torch.tensor(mu), torch.tensor(sg)
+    K = len(mu)
+    g = torch.Generator().manual_seed(23)
+    w = (torch.rand(K, generator=g) - 0.5) * 0.5
+    alpha = torch.rand(K, generator=g) + 0.5
+    gout = torch.randn(B, generator=g)
+    q, d, qm, dm = O.synth_kernel_pool_inputs(B, Lq, Ld, D, seed=11 + D + Ld)
+    assert interaction.kernel_pool_train_supported(Lq, Ld, D, K)
+    s_ref, gq, gd, ga, gw = _oracle_fp64_grads(q, d, qm, dm, mu, sg, alpha, w, ls, gout)
+    args = _c(q, d, qm, dm, mu, sg, w)
+    # the training forward is the inference forward plus stores: identical outputs
+    plain = interaction.kernel_pool(*args, alpha=alpha.to(DEV), log_scale=ls, want_per_kernel=True,
+                                    want_per_kernel_query=True, impl="tcgen05")
+    train = interaction.kernel_pool(*args, alpha=alpha.to(DEV), log_scale=ls, want_per_kernel=True,
+                                    save_for_backward=True)
+    assert torch.equal(plain["score"], train["score"]) and torch.equal(plain["per_kernel"], train["per_kernel"])
+    assert torch.equal(plain["per_kernel_query"], train["per_kernel_query"])
+    res = interaction.kernel_pool_bwd(*args[:6], args[6], alpha.to(DEV), train["per_kernel_query"], gout.to(DEV), ls,
+                                      saved=train["saved"])
+    ref = interaction.kernel_pool_bwd(*args[:6], args[6], alpha.to(DEV), plain["per_kernel_query"], gout.to(DEV), ls)
+    torch.cuda.synchronize()
+    _grad_close(res[0], gq, "grad_q vs fp64")
+    _grad_close(res[1], gd, "grad_d vs fp64")
+    _grad_close(res[2], ga, "grad_alpha vs fp64")
+    _grad_close(res[3], gw, "grad_weight vs fp64")
+    _grad_close(res[0], ref[0], "grad_q vs FFMA backward")
+    _grad_close(res[1], ref[1], "grad_d vs FFMA backward")
+    # masked terms get exactly no gradient
+    assert (res[1].cpu()[dm == 0] == 0).all() and (res[0].cpu()[qm == 0] == 0).all()
+
+
+def test_train_pair_autograd_route_and_determinism():
+    """autograd.kernel_pool takes the tensor-core pair inside its envelope and the FFMA backward outside (Lq > 32,
+    D > 320, doc_gate); two runs of the tensor-core backward are bit-identical."""
+    mu, sg = O.tk_21_kernels()
+    mu, sg = torch.tensor(mu).to(DEV), torch.tensor(sg).to(DEV)
+    w = torch.linspace(-0.3, 0.3, 21).to(DEV)
+    q, d, qm, dm = O.synth_kernel_pool_inputs(300, 30, 200, 300, seed=77)
+    runs = []
+    for _ in range(2):
+        cq, cd = q.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
+        score, _ = autograd.kernel_pool(cq, cd, qm.to(DEV), dm.to(DEV), mu, sg, w, None, 1.0)
+        assert score.grad_fn.tc
+        score.sum().backward()
+        runs.append((cq.grad.clone(), cd.grad.clone()))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    old = autograd.KP_TRAIN_IMPL
+    try:
+        autograd.KP_TRAIN_IMPL = "simt"
+        cq, cd = q.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
+        score, _ = autograd.kernel_pool(cq, cd, qm.to(DEV), dm.to(DEV), mu, sg, w, None, 1.0)
+        assert not score.grad_fn.tc
+        score.sum().backward()
+    finally:
+        autograd.KP_TRAIN_IMPL = old
+    _grad_close(runs[0][0], cq.grad, "grad_q tc vs simt (config 2 shape, 300 pairs)")
+    _grad_close(runs[0][1], cd.grad, "grad_d tc vs simt")
+    q2, d2, qm2, dm2 = O.synth_kernel_pool_inputs(2, 40, 50, 64, seed=5)
+    cq = q2.to(DEV).requires_grad_(True)
+    score, _ = autograd.kernel_pool(cq, d2.to(DEV), qm2.to(DEV), dm2.to(DEV), mu, sg, w, None, 1.0)
+    assert not score.grad_fn.tc
