@@ -330,8 +330,8 @@ class KernelPoolTrainWorkload(KernelPoolWorkload):
     """TK interaction forward + backward (what train.py:504,526 runs per step through autograd): scores, then gradients
     to both embedding tensors, alpha and the bin weights.  Algorithmic bytes per pair: the forward
     reads q, d, masks; the backward reads them again plus S [Lq, K] and writes dq, dd."""
-    launches_per_step = 3   # forward, backward, batch reduction of d weight / d alpha
-    graph_ok = False        # the step runs through torch.autograd
+    launches_per_step = 3   # forward (saves cosines + norms), tcgen05 backward, batch reduction of d weight / d alpha
+    graph_ok = True         # torch.autograd inside the capture (forward + backward of the step, as in whole-step capture)
 
     def __init__(self, rank, dev):
         super().__init__(rank, dev, "tk")
@@ -339,11 +339,13 @@ class KernelPoolTrainWorkload(KernelPoolWorkload):
         self.B = self.pairs = 1024
         self.q, self.d, self.qm, self.dm = self.q[:self.B], self.d[:self.B], self.qm[:self.B], self.dm[:self.B]
         self.metric = "query-doc pairs/sec (TK cosine + RBF kernel pooling forward + backward, D=300)"
-        self.kernel = "kernel_pool_ts_kernel + kernel_pool_bwd_simt"
+        self.kernel = "kernel_pool_ts_kernel<save> + kernel_pool_bwd_tc_kernel"
         fwd = (self.Lq + self.Ld) * self.D * 4 + (self.Lq + self.Ld) * 4 + 4
         bwd = fwd + self.Lq * 21 * 4 * 2 + (self.Lq + self.Ld) * self.D * 4
-        self.alg_bytes = (fwd + bwd) * self.B
-        self.alg_note = "forward %d B/pair + backward %d B/pair (inputs re-read, S saved and re-read, dq/dd written)" % (fwd, bwd)
+        saved = (33 * self.Ld + 32) * 4 * 2   # cosines + inverse norms: written by the forward, read by the backward
+        self.alg_bytes = (fwd + bwd + saved) * self.B
+        self.alg_note = ("forward %d B/pair + backward %d B/pair (inputs re-read, S saved and re-read, dq/dd written) + %d B/pair of "
+                         "saved cosines / norms (written + read)" % (fwd, bwd, saved))
 
     def to_device(self):
         super().to_device()

@@ -40,7 +40,7 @@ def _kernels(sass, needle):
 
 
 @pytest.mark.parametrize("needle", ["maxsim_qm_kernel", "kernel_pool_ts_kernel", "flat_ip_tc_kernel",
-                                    "maxsim_tc_kernel"])
+                                    "maxsim_tc_kernel", "kernel_pool_bwd_tc_kernel", "tkl_ts_kernel"])
 def test_tensor_core_kernels_use_tcgen05_and_tma(sass, needle):
     for name, text in _kernels(sass, needle).items():
         assert "UTCHMMA" in text, f"{name}: no tcgen05.mma (UTCHMMA) in the SASS"
@@ -70,3 +70,14 @@ def test_flat_ip_uses_multicast_in_the_cluster_instantiations(sass):
     ks = _kernels(sass, "flat_ip_tc_kernel")
     multi = [k for k, v in ks.items() if "UTMALDG" in v and ".MULTICAST" in v.upper()]
     assert multi, "no flat-IP instantiation issues a multicast TMA load"
+
+
+def test_kernel_pool_backward_is_a_tensor_core_kernel_with_tma_stores(sass):
+    """Both contractions of the backward as UMMAs (A once from tensor memory, once from shared memory), G written to
+    tensor memory, gradients leaving through TMA stores."""
+    for name, text in _kernels(sass, "kernel_pool_bwd_tc_kernel").items():
+        assert len(re.findall(r"UTCHMMA", text)) >= 2, f"{name}: expected the two UMMA chains"
+        assert re.search(r"\bSTTM\b|STTM\.", text), f"{name}: no tcgen05.st (STTM): G is not written to TMEM"
+        assert "UTMASTG" in text, f"{name}: no TMA tensor store (UTMASTG)"
+        assert "USETMAXREG" in text, f"{name}: setmaxnreg is missing"
+
