@@ -140,6 +140,8 @@ MMB200_API int mmb200_maxsim_fwd_host(const void* q_host, const void* d_host, co
  * Outputs (any of per_kernel / per_kernel_query / cosine may be NULL):
  *   score [B]; per_kernel [B,K] (= P); per_kernel_query [B,Lq,K] (= S, what backward needs);
  *   cosine [B,Lq,Ld] = c_ij * q_mask[i] * d_mask[j] (the reference's secondary output).
+ * impl: MMB200_IMPL_AUTO / _TCGEN05 take the tensor-core kernel for K <= 32, Lq <= 128, cosine == NULL (queries longer
+ * than 32 terms: one pass per block of 32 query rows), _SIMT the FFMA kernel (any Lq).
  * ------------------------------------------------------------------------------------------ */
 MMB200_API int mmb200_kernel_pool_fwd(const float* q, const float* d, const void* q_mask, const void* d_mask,
                                       const float* mu, const float* sigma, const float* alpha,

@@ -41,6 +41,9 @@ struct KpParams {
   // cosines document-row-major [B][Ld][32] (query term contiguous: one 128-byte row per document term, rows >= Lq
   // of a row are 0), then 1 / (|d_j| + eps) [B][Ld], then 1 / (|q_i| + eps) [B][32].  nullptr = do not save.
   float* saved;
+  // tcgen05 forward on a block of <= 32 query rows of a longer query (kernel_pool_ts.cu, Lq > 32): the kernel sees Lq =
+  // rows of the block; the rows sit at q_row0 .. of Lq_total in q, q_mask and per_kernel_query.  0 / Lq otherwise.
+  int32_t q_row0, Lq_total;
   float tf32_comp;   // backward: factor undoing the mean truncation of the raw fp32 operands to tf32 (1 + 2^-11), or 1
 };
 

@@ -172,7 +172,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             uint8_t* st = raws + (size_t)stage * kRawBytes;
             mbar_arrive_expect_tx(&S->raw_full[stage], last ? last_bytes : (uint32_t)kRawBytes);
             tma_load_3d(last ? &tmap_d_last : &tmap_d, st, &S->raw_full[stage], ck * 32, t * 128, (int)p, kEvictFirst);
-            tma_load_3d(&tmap_q, st + kDxBytes, &S->raw_full[stage], ck * 32, 0, (int)p, kEvictLast);
+            tma_load_3d(&tmap_q, st + kDxBytes, &S->raw_full[stage], ck * 32, P.q_row0, (int)p, kEvictLast);
             if (++stage == n_raw) { stage = 0; phase ^= 1u; }
           }
         }
@@ -349,7 +349,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
       for (int k = 0; k < KB; ++k) acc[k] = 0.f;
       uint64_t qraw = 0;
-      if (lane < P.Lq) qraw = qmt != MMB200_MASK_NONE ? mask_raw(P.q_mask, qmt, p * (int64_t)P.Lq + lane) : 1;
+      if (lane < P.Lq) qraw = qmt != MMB200_MASK_NONE ? mask_raw(P.q_mask, qmt, p * (int64_t)P.Lq_total + P.q_row0 + lane) : 1;
       // Short queries: phase B has lane = query row, so a 6-token query would leave 26 lanes of every MUFU instruction
       // idle.  With q_hi = 1 + last unmasked query row, the warp's lanes are dealt as 32 / qp sub-streams of qp query rows
       // (qp = 4, 8, 16 or 32 >= q_hi); sub-stream s takes the document rows r + 16 s, and the sub-streams are added at
@@ -470,7 +470,7 @@ kernel_pool_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           for (int w8 = 0; w8 < 8; ++w8) Ssum += spart[(w8 * KB + k) * 32 + lane];
           float L = 0.f;
           if (k < P.K && lane < P.Lq) {
-            if (P.per_kernel_query) P.per_kernel_query[(p * P.Lq + lane) * (int64_t)P.K + k] = Ssum;
+            if (P.per_kernel_query) P.per_kernel_query[(p * P.Lq_total + P.q_row0 + lane) * (int64_t)P.K + k] = Ssum;
             if (q_live) L = P.log_scale * logf(fmaxf(Ssum * S->alpha[k], P.clamp_min));
           }
 #pragma unroll
@@ -546,15 +546,27 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
   return MMB200_OK;
 }
 
-}  // namespace
+// score[b] = sum over query blocks + bias, per_kernel[b, k] = sum over query blocks (fixed order: deterministic)
+__global__ void kp_combine_query_blocks(const float* __restrict__ score_blk, const float* __restrict__ pk_blk, int nblk, int64_t B,
+                                        int K, float bias, float* __restrict__ score, float* __restrict__ per_kernel) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < B) {
+    float s = 0.f;
+    for (int x = 0; x < nblk; ++x) s += score_blk[x * B + i];
+    score[i] = s + bias;
+  }
+  if (per_kernel && i < B * K) {
+    float s = 0.f;
+    for (int x = 0; x < nblk; ++x) s += pk_blk[x * B * K + i];
+    per_kernel[i] = s;
+  }
+}
 
-int kernel_pool_fwd_ts(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, bool* handled) {
-  *handled = false;
-  if (P.Lq > 32 || P.K > 32 || P.cosine != nullptr || P.D % 4 != 0) return MMB200_OK;
+static int kernel_pool_fwd_ts_block(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream) {
   CUtensorMap tq, td, td_last;
   {
-    const uint64_t dims[3] = {(uint64_t)P.D, (uint64_t)P.Lq, (uint64_t)P.B};
-    const uint64_t strides[2] = {(uint64_t)P.D * 4, (uint64_t)P.Lq * P.D * 4};
+    const uint64_t dims[3] = {(uint64_t)P.D, (uint64_t)P.Lq_total, (uint64_t)P.B};
+    const uint64_t strides[2] = {(uint64_t)P.D * 4, (uint64_t)P.Lq_total * P.D * 4};
     const uint32_t box[3] = {32, 32, 1};
     if (int rc = encode_tensor_map(&tq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, P.q, dims, strides, box,
                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
@@ -574,13 +586,49 @@ int kernel_pool_fwd_ts(const KpParams& P, const DeviceInfo& dev, cudaStream_t st
                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
       return rc;
   }
-  *handled = true;
   // exact instantiations for the reference's kernel counts (KNRM: 11, TK / TKL: 11 or 21 -- no padded activations)
   if (P.K == 11) return launch<11>(P, dev, stream, tq, td, td_last, last_box_rows);
   if (P.K == 21) return launch<21>(P, dev, stream, tq, td, td_last, last_box_rows);
   if (P.K <= 12) return launch<12>(P, dev, stream, tq, td, td_last, last_box_rows);
   if (P.K <= 24) return launch<24>(P, dev, stream, tq, td, td_last, last_box_rows);
   return launch<32>(P, dev, stream, tq, td, td_last, last_box_rows);
+}
+
+}  // namespace
+
+int kernel_pool_fwd_ts(const KpParams& P0, const DeviceInfo& dev, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  constexpr int kMaxBlocks = 4;   // queries up to 128 terms
+  if (P0.Lq > 32 * kMaxBlocks || P0.K > 32 || P0.cosine != nullptr || P0.D % 4 != 0) return MMB200_OK;
+  if (P0.Lq > 32 && P0.saved != nullptr) return MMB200_OK;   // the saved-state layout holds 32 query rows
+  KpParams P = P0;
+  P.q_row0 = 0;
+  P.Lq_total = P0.Lq;
+  *handled = true;
+  if (P0.Lq <= 32) return kernel_pool_fwd_ts_block(P, dev, stream);
+  // Longer queries: one pass of the same kernel per block of 32 query rows (the document tiles are streamed once per
+  // block -- still several times faster than the FFMA kernel), per-block scores and per-kernel sums added afterwards.
+  const int nblk = (P0.Lq + 31) / 32;
+  float* tmp = nullptr;
+  const size_t n_tmp = (size_t)nblk * P0.B * (1 + P0.K);
+  MMB_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp), n_tmp * sizeof(float), stream));
+  int rc = MMB200_OK;
+  for (int x = 0; x < nblk && rc == MMB200_OK; ++x) {
+    P.q_row0 = 32 * x;
+    P.Lq = std::min(32, P0.Lq - 32 * x);
+    P.score = tmp + (size_t)x * P0.B;
+    P.per_kernel = tmp + (size_t)nblk * P0.B + (size_t)x * P0.B * P0.K;
+    P.bias = 0.f;
+    rc = kernel_pool_fwd_ts_block(P, dev, stream);
+  }
+  if (rc == MMB200_OK) {
+    const int64_t n = std::max<int64_t>(P0.B * (P0.per_kernel ? P0.K : 1), P0.B);
+    kp_combine_query_blocks<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tmp, tmp + (size_t)nblk * P0.B, nblk, P0.B, P0.K, P0.bias,
+                                                                              P0.score, P0.per_kernel);
+    if (cudaGetLastError() != cudaSuccess) { set_error("kp_combine_query_blocks launch failed"); rc = MMB200_ERR_CUDA; }
+  }
+  MMB_CHECK_CUDA(cudaFreeAsync(tmp, stream));
+  return rc;
 }
 
 }  // namespace mmb

@@ -188,7 +188,10 @@ def test_baseline_cfg2_size_properties():
                                    # one 16-column group only; last chunk exactly 16 columns; full last tile; 4 tiles with a
                                    # 1-row last tile; more pairs than SMs with a short single tile
                                    (5, 30, 100, 16, "tk21"), (5, 12, 70, 48, "tk11"), (3, 32, 128, 64, "knrm11"),
-                                   (2, 30, 385, 300, "tk21"), (333, 30, 40, 300, "tk21")])
+                                   (2, 30, 385, 300, "tk21"), (333, 30, 40, 300, "tk21"),
+                                   # queries longer than 32 terms: one pass of the kernel per block of 32 query rows
+                                   (3, 40, 200, 300, "tk21"), (5, 33, 50, 64, "tk11"), (2, 64, 130, 32, "knrm11"),
+                                   (2, 100, 60, 100, "tk11")])
 def test_tcgen05_forward_vs_oracle(shape):
     """The 2-pass TF32 (hi/lo split, stacked-N) tensor-core forward against the fp32 oracle."""
     B, Lq, Ld, D, kind = shape
