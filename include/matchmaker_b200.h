@@ -189,11 +189,11 @@ MMB200_API int mmb200_kernel_pool_bwd_ex(const float* q, const float* d, const v
                                          void* stream);
 
 /* Training pair on the tensor cores (the step of train.py:330-360 for KNRM / TK: forward, loss, backward).
- *   mmb200_kernel_pool_fwd_train = mmb200_kernel_pool_fwd_ex (tcgen05 kernel, no doc_gate) that additionally leaves
+ *   mmb200_kernel_pool_fwd_train = mmb200_kernel_pool_fwd_ex (tcgen05 kernel; doc_gate as there, or NULL) that additionally leaves
  *   `saved` for the backward: mmb200_kernel_pool_saved_floats(B, Ld) = B * (33 * Ld + 32) floats, 16-byte aligned
  *   (cosines document-row-major [B][Ld][32], then 1 / (|d_j| + eps) [B][Ld], then 1 / (|q_i| + eps) [B][32]); the
  *   layout is private to the pair of calls.
- *   mmb200_kernel_pool_bwd_saved = mmb200_kernel_pool_bwd_ex computed from `saved` with both contractions
+ *   mmb200_kernel_pool_bwd_saved = mmb200_kernel_pool_bwd_ex (doc_gate / grad_gate as there, or NULL) computed from `saved` with both contractions
  *   (G q^ and G^T d^) as kind::tf32 UMMAs on the raw fp32 tiles; gradients agree with the fp32 expression to a few
  *   1e-4 relative (tf32 operands; the reference trains under fp16 autocast).  grad_q / grad_d must be 16-byte aligned.
  *   Envelope: mmb200_kernel_pool_train_tc_supported(Lq, Ld, D, K) != 0  (Lq <= 32, K <= 32, D % 4 == 0, D <= 320);
@@ -201,14 +201,15 @@ MMB200_API int mmb200_kernel_pool_bwd_ex(const float* q, const float* d, const v
 MMB200_API int32_t mmb200_kernel_pool_train_tc_supported(int32_t Lq, int32_t Ld, int32_t D, int32_t K);
 MMB200_API int64_t mmb200_kernel_pool_saved_floats(int64_t B, int32_t Ld);
 MMB200_API int mmb200_kernel_pool_fwd_train(const float* q, const float* d, const void* q_mask, const void* d_mask,
-                                            const float* mu, const float* sigma, const float* alpha, const float* weight,
-                                            float* score, float* per_kernel, float* per_kernel_query, float* saved,
+                                            const float* doc_gate, const float* mu, const float* sigma, const float* alpha,
+                                            const float* weight, float* score, float* per_kernel, float* per_kernel_query, float* saved,
                                             int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K, float log_scale,
                                             float clamp_min, float score_bias, int32_t mask_dtype, void* stream);
 MMB200_API int mmb200_kernel_pool_bwd_saved(const float* q, const float* d, const void* q_mask, const void* d_mask,
-                                            const float* mu, const float* sigma, const float* alpha, const float* weight,
-                                            const float* per_kernel_query, const float* saved, const float* grad_score,
-                                            float* grad_q, float* grad_d, float* grad_alpha, float* grad_weight,
+                                            const float* doc_gate, const float* mu, const float* sigma, const float* alpha,
+                                            const float* weight, const float* per_kernel_query, const float* saved,
+                                            const float* grad_score, float* grad_q, float* grad_d, float* grad_gate,
+                                            float* grad_alpha, float* grad_weight,
                                             float* workspace, int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K,
                                             float log_scale, float clamp_min, int32_t mask_dtype, void* stream);
 

@@ -45,7 +45,7 @@ class _KernelPool(torch.autograd.Function):
         # needs_input_grad (not tensor.requires_grad: parameters always require grad, also under no_grad)
         need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 6, 7, 9))
         # training step on the tensor cores when the shape allows it (KP_TRAIN_IMPL = "simt" keeps the FFMA backward)
-        tc = (need_grad and doc_gate is None and KP_TRAIN_IMPL != "simt"
+        tc = (need_grad and KP_TRAIN_IMPL != "simt"
               and interaction.kernel_pool_train_supported(q.shape[1], d.shape[1], q.shape[2], mu.numel()))
         out = interaction.kernel_pool(q, d, q_mask, d_mask, mu, sigma, weight, alpha, log_scale,
                                       want_per_kernel=True, want_per_kernel_query=need_grad, doc_gate=doc_gate,

@@ -542,7 +542,8 @@ extern "C" int32_t mmb200_kernel_pool_train_tc_supported(int32_t Lq, int32_t Ld,
 extern "C" int64_t mmb200_kernel_pool_saved_floats(int64_t B, int32_t Ld) { return mmb::kp_saved_floats(B, Ld); }
 
 extern "C" int mmb200_kernel_pool_fwd_train(const float* q, const float* d, const void* q_mask, const void* d_mask,
-                                            const float* mu, const float* sigma, const float* alpha, const float* weight,
+                                            const float* doc_gate, const float* mu, const float* sigma, const float* alpha,
+                                            const float* weight,
                                             float* score, float* per_kernel, float* per_kernel_query, float* saved,
                                             int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K, float log_scale,
                                             float clamp_min, float score_bias, int32_t mask_dtype, void* stream_) {
@@ -552,14 +553,15 @@ extern "C" int mmb200_kernel_pool_fwd_train(const float* q, const float* d, cons
     set_error("kernel_pool_fwd_train: shape outside the tcgen05 training envelope (Lq <= 32, K <= 32, D % 4 == 0, D <= 320)");
     return MMB200_ERR_UNSUPPORTED;
   }
-  return kp_fwd_impl(q, d, q_mask, d_mask, nullptr, mu, sigma, alpha, weight, score, per_kernel, per_kernel_query, nullptr,
+  return kp_fwd_impl(q, d, q_mask, d_mask, doc_gate, mu, sigma, alpha, weight, score, per_kernel, per_kernel_query, nullptr,
                      saved, B, Lq, Ld, D, K, log_scale, clamp_min, score_bias, mask_dtype, MMB200_IMPL_TCGEN05, stream_);
 }
 
 extern "C" int mmb200_kernel_pool_bwd_saved(const float* q, const float* d, const void* q_mask, const void* d_mask,
-                                            const float* mu, const float* sigma, const float* alpha, const float* weight,
-                                            const float* per_kernel_query, const float* saved, const float* grad_score,
-                                            float* grad_q, float* grad_d, float* grad_alpha, float* grad_weight,
+                                            const float* doc_gate, const float* mu, const float* sigma, const float* alpha,
+                                            const float* weight, const float* per_kernel_query, const float* saved,
+                                            const float* grad_score, float* grad_q, float* grad_d, float* grad_gate,
+                                            float* grad_alpha, float* grad_weight,
                                             float* workspace, int64_t B, int32_t Lq, int32_t Ld, int32_t D, int32_t K,
                                             float log_scale, float clamp_min, int32_t mask_dtype, void* stream_) {
   using namespace mmb;
@@ -568,8 +570,8 @@ extern "C" int mmb200_kernel_pool_bwd_saved(const float* q, const float* d, cons
     set_error("kernel_pool_bwd_saved: shape outside the tcgen05 training envelope (Lq <= 32, K <= 32, D % 4 == 0, D <= 320)");
     return MMB200_ERR_UNSUPPORTED;
   }
-  return kp_bwd_impl(q, d, q_mask, d_mask, nullptr, mu, sigma, alpha, weight, per_kernel_query, saved, grad_score, grad_q,
-                     grad_d, nullptr, grad_alpha, grad_weight, workspace, B, Lq, Ld, D, K, log_scale, clamp_min, mask_dtype,
+  return kp_bwd_impl(q, d, q_mask, d_mask, doc_gate, mu, sigma, alpha, weight, per_kernel_query, saved, grad_score, grad_q,
+                     grad_d, grad_gate, grad_alpha, grad_weight, workspace, B, Lq, Ld, D, K, log_scale, clamp_min, mask_dtype,
                      stream_);
 }
 

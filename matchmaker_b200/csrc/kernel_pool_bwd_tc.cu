@@ -90,7 +90,8 @@ struct BwShared {
   float rsq[2][32];                  // 1 / (|q_i| + eps) of the pair
   float rowsc[2][3][128];            // [G slot][rsd | projection, query rows 0-15 | 16-31][tile row]
   float ci_part[4][8][16];           // [pair & 3][G warp][query row of its half]: sum_j G_ij c_ij over the warp's rows
-  float mu[32], a[32], is2[32], alpha[32], w[32];
+  float mu[32], a[32], is2[32], sig2[32], alpha[32], w[32];
+  float hgate[2][2][128];            // [G slot][query-row half][tile row]: d loss / d gate of the document term (GATE)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -129,7 +130,7 @@ __device__ __forceinline__ float ex2f(float x) {
   } while (0)
 #endif
 
-template <int KB>
+template <int KB, bool GATE>
 __global__ void __launch_bounds__(kThreads, 1)
 kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
                           const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_dd,
@@ -190,6 +191,7 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     S->mu[t] = ok ? P.mu[t] : 0.f;
     S->a[t] = ok ? sqrtf(0.5f * 1.4426950408889634f) / sg : 0.f;
     S->is2[t] = ok ? 1.0f / (sg * sg) : 0.f;
+    S->sig2[t] = ok ? sg * sg : 0.f;
     S->alpha[t] = ok ? (P.alpha ? P.alpha[t] : 1.f) : 1.f;
     S->w[t] = ok ? P.weight[t] : 0.f;
   }
@@ -369,6 +371,10 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
           tc_fence_after_sync();
           const float rsd = S->rowsc[g][0][row] * P.tf32_comp;
           const float pr = S->rowsc[g][1][row] + S->rowsc[g][2][row];
+          if constexpr (GATE) {
+            if (s == 0 && P.grad_gate && t * 128 + row < P.Ld)
+              P.grad_gate[p * (int64_t)P.Ld + t * 128 + row] = S->hgate[g][0][row] + S->hgate[g][1][row];
+          }
           uint8_t* stage = ring + (size_t)slot * stage_bytes;
           for (int b = 0; b < nb; ++b) {
             uint32_t r[32];
@@ -454,12 +460,14 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         if (warp_live) {
 #pragma unroll
           for (int x = 0; x < 16; ++x) G[x] = 0.f;
+          float H[4] = {0.f, 0.f, 0.f, 0.f};   // GATE: sum_i sum_k coef_ik K_ijk = d loss / d gate_j (four partial chains)
           if (any_valid && 16 * hh < P.Lq) {   // warp-uniform
             // kernel by kernel, the 16 query rows side by side: 16 independent chains per step, centre and width of the
             // kernel as warp-uniform operands, the coef row of the kernel as four broadcast 16-byte loads
 #pragma unroll 3
             for (int k = 0; k < KB; ++k) {
               const float mu_k = S->mu[k], a_k = S->a[k];
+              const float sig2_k = GATE ? S->sig2[k] : 0.f;
               const float4* Tk = reinterpret_cast<const float4*>(&S->T[pb][k][16 * hh]);
 #pragma unroll
               for (int x4 = 0; x4 < 4; ++x4) {
@@ -470,16 +478,24 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
                   const int x = 4 * x4 + y;
                   const float diff = mu_k - c[x];
                   const float u = diff * a_k;
-                  G[x] = fmaf(Tv[y] * ex2f(-u * u), diff, G[x]);
+                  const float te = Tv[y] * ex2f(-u * u);
+                  G[x] = fmaf(te, diff, G[x]);
+                  if constexpr (GATE) H[y] = fmaf(te, sig2_k, H[y]);
                 }
               }
             }
           }
           float cpr = 0.f;
           float gc[16];
+          float gate_j = 1.f;
+          if constexpr (GATE) {
+            const float gv = valid ? P.gate[p * (int64_t)P.Ld + j] : 0.f;
+            gate_j = fmaxf(gv, 0.f);   // the forward counts a negative gate as 0: relu'(gate) = 0 there
+            S->hgate[g][hh][row] = (valid && gv >= 0.f) ? (H[0] + H[1]) + (H[2] + H[3]) : 0.f;
+          }
 #pragma unroll
           for (int x = 0; x < 16; ++x) {
-            G[x] = valid ? G[x] : 0.f;
+            G[x] = valid ? G[x] * gate_j : 0.f;
             gc[x] = G[x] * c[x];
             cpr += gc[x];
           }
@@ -611,7 +627,7 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
 }
 #undef KPB_T
 
-template <int KB>
+template <int KB, bool GATE>
 int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& td,
            const CUtensorMap& tdq, const CUtensorMap& tdd) {
   constexpr int KBP = (KB + 3) & ~3;
@@ -630,7 +646,7 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
   const size_t smem = fixed + (size_t)n_stages * stage_bytes;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
-    MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_bwd_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_bwd_tc_kernel<KB, GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)((size_t)dev.max_smem_optin)));
     attr_set = true;
   }
@@ -643,7 +659,7 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
     MMB_CHECK_CUDA(cudaMemset(prof, 0, 704 * sizeof(long long)));
   }
 #endif
-  kernel_pool_bwd_tc_kernel<KB><<<grid, kThreads, smem, stream>>>(tq, td, tdq, tdd, P, n_stages, stage_boxes, mn_sbo, prof);
+  kernel_pool_bwd_tc_kernel<KB, GATE><<<grid, kThreads, smem, stream>>>(tq, td, tdq, tdd, P, n_stages, stage_boxes, mn_sbo, prof);
   MMB_CHECK_CUDA(cudaGetLastError());
 #ifdef MMB200_ENABLE_PROF
   if (do_prof) {
@@ -691,7 +707,7 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
 
 int kernel_pool_bwd_tc(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, bool* handled) {
   *handled = false;
-  if (P.saved == nullptr || P.Lq > 32 || P.K > 32 || P.D % 4 != 0 || P.D > kMaxD || P.gate != nullptr || P.grad_gate != nullptr)
+  if (P.saved == nullptr || P.Lq > 32 || P.K > 32 || P.D % 4 != 0 || P.D > kMaxD || (P.grad_gate != nullptr && P.gate == nullptr))
     return MMB200_OK;
   if (((reinterpret_cast<uintptr_t>(P.grad_q) | reinterpret_cast<uintptr_t>(P.grad_d) | reinterpret_cast<uintptr_t>(P.saved)) & 15) != 0)
     return MMB200_OK;
@@ -719,11 +735,18 @@ int kernel_pool_bwd_tc(const KpParams& P, const DeviceInfo& dev, cudaStream_t st
       return rc;
   }
   *handled = true;
-  if (P.K == 11) return launch<11>(P, dev, stream, tq, td, tdq, tdd);
-  if (P.K == 21) return launch<21>(P, dev, stream, tq, td, tdq, tdd);
-  if (P.K <= 12) return launch<12>(P, dev, stream, tq, td, tdq, tdd);
-  if (P.K <= 24) return launch<24>(P, dev, stream, tq, td, tdq, tdd);
-  return launch<32>(P, dev, stream, tq, td, tdq, tdd);
+  if (P.gate) {   // TK-Sparse: gated activations, d loss / d gate
+    if (P.K == 11) return launch<11, true>(P, dev, stream, tq, td, tdq, tdd);
+    if (P.K == 21) return launch<21, true>(P, dev, stream, tq, td, tdq, tdd);
+    if (P.K <= 12) return launch<12, true>(P, dev, stream, tq, td, tdq, tdd);
+    if (P.K <= 24) return launch<24, true>(P, dev, stream, tq, td, tdq, tdd);
+    return launch<32, true>(P, dev, stream, tq, td, tdq, tdd);
+  }
+  if (P.K == 11) return launch<11, false>(P, dev, stream, tq, td, tdq, tdd);
+  if (P.K == 21) return launch<21, false>(P, dev, stream, tq, td, tdq, tdd);
+  if (P.K <= 12) return launch<12, false>(P, dev, stream, tq, td, tdq, tdd);
+  if (P.K <= 24) return launch<24, false>(P, dev, stream, tq, td, tdq, tdd);
+  return launch<32, false>(P, dev, stream, tq, td, tdq, tdd);
 }
 
 }  // namespace mmb

@@ -198,7 +198,7 @@ def kernel_pool(q: torch.Tensor, d: torch.Tensor, q_mask: torch.Tensor, d_mask: 
     cikm20_tk_sparse.py:135); ``clamp_min`` / ``bias`` are the 1e-4 floor and the Linear bias of IDCM's ESM scorer
     (sigir21_idcm.py:185-186).
 
-    ``save_for_backward=True`` (shapes for which :func:`kernel_pool_train_supported` holds, no ``doc_gate``) runs the
+    ``save_for_backward=True`` (shapes for which :func:`kernel_pool_train_supported` holds) runs the
     training forward: the result additionally carries "saved", the opaque state the tensor-core backward consumes
     (:func:`kernel_pool_bwd` with ``saved=``), and "per_kernel_query"."""
     dev = _require_cuda(q, d, q_mask, d_mask, mu, sigma, weight, alpha, doc_gate)
@@ -222,13 +222,13 @@ def kernel_pool(q: torch.Tensor, d: torch.Tensor, q_mask: torch.Tensor, d_mask: 
         gate = _f32c(doc_gate).reshape(B, Ld)
     lib = _lib.load()
     if save_for_backward:
-        if gate is not None or want_cosine or not kernel_pool_train_supported(Lq, Ld, D, K):
+        if want_cosine or not kernel_pool_train_supported(Lq, Ld, D, K):
             raise _lib.MatchmakerB200Error("kernel_pool(save_for_backward=True): outside the tensor-core training envelope")
         if pkq is None:
             pkq = torch.empty((B, Lq, K), dtype=torch.float32, device=dev)
         saved = torch.empty(int(lib.mmb200_kernel_pool_saved_floats(B, Ld)), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            rc = lib.mmb200_kernel_pool_fwd_train(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(mu), _ptr(sigma),
+            rc = lib.mmb200_kernel_pool_fwd_train(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(gate), _ptr(mu), _ptr(sigma),
                                                   _ptr(alpha), _ptr(weight), _ptr(score), _ptr(pk), _ptr(pkq), _ptr(saved),
                                                   B, Lq, Ld, D, K, float(log_scale), float(clamp_min), float(bias), mcode,
                                                   _stream(dev))
@@ -271,15 +271,15 @@ def kernel_pool_bwd(q, d, q_mask, d_mask, mu, sigma, weight, alpha, per_kernel_q
     gg = None if doc_gate is None else torch.empty((B, Ld), dtype=torch.float32, device=dev)
     lib = _lib.load()
     if saved is not None:
-        if doc_gate is not None:
-            raise _lib.MatchmakerB200Error("kernel_pool_bwd(saved=...): doc_gate is not supported by the tensor-core backward")
         with torch.cuda.device(dev):
-            rc = lib.mmb200_kernel_pool_bwd_saved(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(mu), _ptr(sigma),
+            rc = lib.mmb200_kernel_pool_bwd_saved(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(gate), _ptr(mu), _ptr(sigma),
                                                   _ptr(alpha_c), _ptr(weight), _ptr(per_kernel_query.contiguous()),
-                                                  _ptr(saved), _ptr(_f32c(grad_score)), _ptr(gq), _ptr(gd), _ptr(ga),
+                                                  _ptr(saved), _ptr(_f32c(grad_score)), _ptr(gq), _ptr(gd), _ptr(gg), _ptr(ga),
                                                   _ptr(gw), _ptr(ws), B, Lq, Ld, D, K, float(log_scale), float(clamp_min),
                                                   mcode, _stream(dev))
         _lib.check(rc, "mmb200_kernel_pool_bwd_saved")
+        if doc_gate is not None:
+            return gq, gd, (ga if alpha is not None else None), gw, gg
         return gq, gd, (ga if alpha is not None else None), gw
     with torch.cuda.device(dev):
         rc = lib.mmb200_kernel_pool_bwd_ex(_ptr(q), _ptr(d), _ptr(q_mask), _ptr(d_mask), _ptr(gate), _ptr(mu), _ptr(sigma),

@@ -100,8 +100,12 @@ def test_conv_knrm_class_matches_reference_golden():
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
 
 
-def test_gate_backward_vs_fp64_autograd_of_oracle():
-    B, Lq, Ld, D, K = 4, 9, 37, 32, 11
+@pytest.mark.parametrize("train_impl", ["auto", "simt"])   # tensor-core training pair / FFMA backward
+@pytest.mark.parametrize("shape", [(4, 9, 37, 32), (5, 30, 200, 300), (150, 12, 130, 64)])
+def test_gate_backward_vs_fp64_autograd_of_oracle(shape, train_impl, monkeypatch):
+    monkeypatch.setattr(autograd, "KP_TRAIN_IMPL", train_impl)
+    B, Lq, Ld, D = shape
+    K = 11
     g = torch.Generator().manual_seed(3)
     mu = torch.tensor([1.0, 0.9, 0.7, 0.5, 0.3, 0.1, -0.1, -0.3, -0.5, -0.7, -0.9])
     sg = torch.full((K,), 0.1)
@@ -118,6 +122,7 @@ def test_gate_backward_vs_fp64_autograd_of_oracle():
     cq, cd = q.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
     cg, cw, ca = gate.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True), alpha.to(DEV).requires_grad_(True)
     score, _ = autograd.kernel_pool(cq, cd, qm.to(DEV), dm.to(DEV), mu.to(DEV), sg.to(DEV), cw, ca, 1.0, doc_gate=cg)
+    assert score.grad_fn.tc == (train_impl == "auto")
     assert_close_rel(score, s64.float(), what="score")
     score.backward(gout.to(DEV))
 
