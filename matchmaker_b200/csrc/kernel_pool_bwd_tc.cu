@@ -644,11 +644,12 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
     return MMB200_ERR_UNSUPPORTED;
   }
   const size_t smem = fixed + (size_t)n_stages * stage_bytes;
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
+  static bool attr_set[64] = {};   // per instantiation and device (the attribute is per device)
+  const int di = dev.device & 63;
+  if (!attr_set[di]) {
     MMB_CHECK_CUDA(cudaFuncSetAttribute(kernel_pool_bwd_tc_kernel<KB, GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)((size_t)dev.max_smem_optin)));
-    attr_set = true;
+    attr_set[di] = true;
   }
   const int grid = (int)std::min<int64_t>(dev.sm_count, P.B);
   long long* prof = nullptr;

@@ -292,6 +292,9 @@ TRAIN_SHAPES = [  # B, Lq, Ld, D, K-kind
     (6, 30, 300, 100, "tk21"),      # three tiles: the G groups alternate within and across pairs
     (2, 2, 3, 4, "tk11"),           # smallest embedding (one 16-byte row)
     (3, 30, 40, 320, "k32"),        # widest supported embedding, padded kernel count
+    (2, 30, 1000, 64, "tk11"),      # eight document tiles per pair
+    (3, 5, 70, 8, "tk11"),          # a quarter of one feature box
+    (1, 32, 256, 128, "tk21"),      # a single pair: one CTA
 ]
 
 
