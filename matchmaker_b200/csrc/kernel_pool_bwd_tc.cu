@@ -12,7 +12,7 @@
 //     dq_i  likewise with q^_i . dq^_i = sum_j G_ij c_ij (per-warp partial sums, added in a fixed order).
 //
 // The two contractions are the whole cost of the FFMA backward (kernel_pool.cu: 1.13 ms for 1024 TK pairs, 0.08 of the
-// HBM ceiling; this kernel: 0.17 ms, 0.50).  Here both run as kind::tf32 UMMAs straight on the RAW fp32 tiles TMA delivers -- the 1 / norm factors
+// HBM ceiling; this kernel: 0.173 ms, 0.50; 4096 pairs: 0.633 ms, 0.55).  Here both run as kind::tf32 UMMAs straight on the RAW fp32 tiles TMA delivers -- the 1 / norm factors
 // are folded into G, so no converted copy of Q or D is ever written:
 //
 //   GEMM 1  dd^[128 doc rows x 64 features] = G1[128 x 32] (A from TENSOR MEMORY, thread = document row wrote it)
@@ -24,9 +24,11 @@
 //
 // The cosines are not recomputed: the training forward (kernel_pool_ts_kernel<.., SAVE>) leaves them document-row-major
 // together with the inverse norms (KpParams::saved), 26 KB per TK pair against 277 KB of embeddings.
-// The document gradient of a stage is finished in place: the epilogue thread (= document row) combines the accumulator
-// row with its own raw row of the box still in shared memory, overwrites it and the box leaves by TMA store; the query
-// gradient likewise from the query tile at the end of the pair.
+// A stage of the ring = two document boxes + the two query boxes of the same 64 features (40 KB; the query boxes come
+// again for every document tile: L2 hits) -- no resident query tile, four stages fit.  The document gradient of a stage is
+// finished in place: the epilogue thread (= document row) combines the accumulator row with its own raw row of the box
+// still in shared memory, overwrites it and the box leaves by TMA store; the query gradient walks its 32-feature chunks
+// through four 4 KB staging boxes the same way at the end of the pair.
 //
 // Operand precision: G is rounded to tf32 (cvt.rna); the raw tiles are truncated by the tensor core (low 13 mantissa
 // bits dropped, mean relative shrink 0.72 * 2^-11), which KpParams::tf32_comp undoes on average.  Gradients agree with
@@ -34,14 +36,15 @@
 // the reference itself trains under fp16 autocast (train.py:330-348).
 //
 // Per CTA (persistent, one per SM, 640 threads; registers re-dealt per warpgroup with setmaxnreg):
-//   warp 0       TMA producer: query tile (nch boxes [32 x 32]) once per pair, document stages (2 boxes [128 x 32])
+//   warp 0       TMA producer: stages of 2 document boxes [128 x 32] + 2 query boxes [32 x 32], four-slot ring
 //   warp 1       UMMA issuer
 //   warp 3       store agent: TMA stores of finished document-gradient stages, stage release
 //   warp 2       per pair: coef table T_ik = coef_ik / sigma_k^2, d weight / d alpha partial sums (from S only)
 //   warps 4-7    document-gradient epilogue (thread = document row = TMEM lane)
 //   warps 8-15   G: warp (quarter, half) = 32 document rows x 16 query rows of every tile; tiles alternate between two
 //                G slots (TMEM columns + shared-memory atoms) so the next tile is prepared while the current one streams
-//   warp 16      query-gradient epilogue (lane = query row = TMEM lane)
+//   warp 16      query-gradient epilogue (lane = query row = TMEM lane): drains the accumulator stage by stage, own small
+//                TMA pipeline (raw query box in, finished gradient box out)
 //
 // TMEM map (512 columns): [0,320) dq^ accumulator (D <= 320); [320,448) 2 dd^ accumulators of 64; [448,512) G1, 2 x 32.
 #include <algorithm>
@@ -64,6 +67,7 @@ constexpr int kQBoxBytes = 32 * 128;       // query box [32 rows][32 fp32]
 constexpr int kG2AtomBytes = 32 * 128;     // G2^T atom: 32 query rows x 32 document rows (K-major, 128-byte rows)
 constexpr int kG2Bytes = 4 * kG2AtomBytes; // one 128-row tile
 constexpr int kMaxStages = 8;
+constexpr int kDqSlots = 4;               // staging boxes of the query-gradient epilogue (load, finish in place, store)
 constexpr int kDdAcc = 2;
 constexpr int kColDq = 0, kColDd = 320, kColG1 = 448;
 constexpr int kMaxD = 320;
@@ -80,9 +84,9 @@ struct BwShared {
   uint64_t store_ready[kMaxStages];   // document epilogue -> store agent: the stage holds finished gradient boxes
   uint64_t acc_full[kDdAcc], acc_empty[kDdAcc];
   uint64_t g_full[2], g_empty[2];
-  uint64_t q_full[2], q_empty[2];
   uint64_t coef_full[2], coef_empty[2];
   uint64_t dq_full;
+  uint64_t dqs_full[kDqSlots];   // TMA -> query epilogue: the query box of a chunk has landed in its staging slot
   uint64_t dq_empty[10];   // per stage of a tile: its 64 (32) accumulator columns have been drained by the query epilogue
   uint32_t tmem_base;
   uint32_t pad;
@@ -146,13 +150,13 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int nch = (P.D + 31) / 32;
-  const int stage_bytes = stage_boxes * kBoxBytes;
-  const int qbuf_bytes = nch * kQBoxBytes;
+  const int stage_bytes = stage_boxes * (kBoxBytes + kQBoxBytes);   // [document boxes | the query boxes of the same features]
+  const int stage_q_off = stage_boxes * kBoxBytes;
   // G2 first: the M = 128 UMMA reads 96 idle A rows past each 32-row atom (up to 12 KB past the slot) -- into the ring
   uint8_t* g2 = smem;                                         // [2][4 atoms][32 rows][128 B]
   uint8_t* ring = g2 + 2 * kG2Bytes;                          // [n_stages][2 boxes]
-  uint8_t* qbuf = ring + (size_t)n_stages * stage_bytes;      // [2][nch boxes]
-  Shared* S = reinterpret_cast<Shared*>(qbuf + 2 * (size_t)qbuf_bytes);
+  uint8_t* dqs = ring + (size_t)n_stages * stage_bytes;       // [kDqSlots] query boxes of the query-gradient epilogue
+  Shared* S = reinterpret_cast<Shared*>(dqs + kDqSlots * kQBoxBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = (P.Ld + 127) / 128;
@@ -164,8 +168,8 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmap_q);
     prefetch_tensormap(&tmap_d);
-    prefetch_tensormap(&tmap_dq);
     prefetch_tensormap(&tmap_dd);
+    prefetch_tensormap(&tmap_dq);
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(&S->raw_full[s], 1);
       mbar_init(&S->raw_empty[s], 1);
@@ -175,12 +179,11 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     for (int s = 0; s < 2; ++s) {
       mbar_init(&S->g_full[s], 8);
       mbar_init(&S->g_empty[s], 1 + kDdWarps);      // tcgen05.commit of the tile's last stage + the document-epilogue warps
-      mbar_init(&S->q_full[s], 1);
-      mbar_init(&S->q_empty[s], 1);
       mbar_init(&S->coef_full[s], 1);
       mbar_init(&S->coef_empty[s], 8);
     }
     mbar_init(&S->dq_full, 1);
+    for (int s = 0; s < kDqSlots; ++s) mbar_init(&S->dqs_full[s], 1);
     for (int s = 0; s < 10; ++s) mbar_init(&S->dq_empty[s], 1);
     fence_barrier_init();
   }
@@ -210,27 +213,20 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         uint32_t ph = 0;
         for (int64_t p = p_begin; p < p_end; ++p) {
           const int pi = (int)(p - p_begin);
-          auto load_q = [&](int64_t pp, int ppi) {
-            const int qb = ppi & 1;
-            KPB_T(0, mbar_wait<true>(&S->q_empty[qb], (uint32_t)(((ppi >> 1) & 1) ^ 1)));
-            mbar_arrive_expect_tx(&S->q_full[qb], (uint32_t)qbuf_bytes);
-            for (int c = 0; c < nch; ++c)
-              tma_load_3d(&tmap_q, qbuf + (size_t)qb * qbuf_bytes + (size_t)c * kQBoxBytes, &S->q_full[qb], c * 32, 0, (int)pp,
-                          kEvictNormal);
-          };
-          if (pi == 0) load_q(p, 0);
           for (int t = 0; t < tiles; ++t)
             for (int s = 0; s < spt; ++s) {
-              // the next pair's query tile goes out half-way through this pair: by then the query epilogue of the pair
-              // before this one (it runs while this pair's first stages stream) has freed the buffer
-              if (t * spt + s == (tiles * spt) / 2 && p + 1 < p_end) load_q(p + 1, pi + 1);
               const int nb = min(stage_boxes, nch - s * stage_boxes);
               KPB_T(1, mbar_wait<true>(&S->raw_empty[slot], ph ^ 1u));
               KPB_TRACE(pi * tiles * spt + t * spt + s, 0);
-              mbar_arrive_expect_tx(&S->raw_full[slot], (uint32_t)(nb * kBoxBytes));
-              for (int b = 0; b < nb; ++b)
+              mbar_arrive_expect_tx(&S->raw_full[slot], (uint32_t)(nb * (kBoxBytes + kQBoxBytes)));
+              for (int b = 0; b < nb; ++b) {
                 tma_load_3d(&tmap_d, ring + (size_t)slot * stage_bytes + (size_t)b * kBoxBytes, &S->raw_full[slot],
                             (s * stage_boxes + b) * 32, t * 128, (int)p, kEvictFirst);
+                // the query boxes of the same features travel with the stage (a second time per document tile: L2 hits) --
+                // no resident query tile, the shared memory it took is a fourth ring slot
+                tma_load_3d(&tmap_q, ring + (size_t)slot * stage_bytes + stage_q_off + (size_t)b * kQBoxBytes, &S->raw_full[slot],
+                            (s * stage_boxes + b) * 32, 0, (int)p, kEvictLast);
+              }
               if (++slot == n_stages) { slot = 0; ph ^= 1u; }
             }
         }
@@ -242,9 +238,7 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       int tseq = 0;
       for (int64_t p = p_begin; p < p_end; ++p) {
         const int pi = (int)(p - p_begin), qb = pi & 1;
-        KPB_T(0, mbar_wait<true>(&S->q_full[qb], (uint32_t)((pi >> 1) & 1)));
         tc_fence_after_sync();
-        const uint32_t qaddr = smem_u32(qbuf + (size_t)qb * qbuf_bytes);
         for (int t = 0; t < tiles; ++t, ++tseq) {
           const int g = tseq & 1;
           if (lane == 0) KPB_TTRACE(tseq, 0);
@@ -266,8 +260,8 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
             tc_fence_after_sync();
             const uint32_t dd_acc = tmem_base + (uint32_t)(kColDd + a * 64);
             const uint32_t dq_acc = tmem_base + (uint32_t)(kColDq + s * stage_boxes * 32);
-            const uint32_t qbox = qaddr + (uint32_t)(s * stage_boxes * kQBoxBytes);
             const uint32_t dbox = smem_u32(ring + (size_t)slot * stage_bytes);
+            const uint32_t qbox = dbox + (uint32_t)stage_q_off;
             const bool last_s = s == spt - 1;
             if (elect_one_sync()) {
 #pragma unroll
@@ -555,25 +549,43 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     // ------------------------------- query-gradient epilogue (warp 16) ---------------
     setmaxnreg_dec<kRegsDq>();
     if (warp == kDqWarp) {
+      // The query gradient is 36 KB per pair against 240 KB of document gradient: no resident query tile (its shared memory
+      // is the ring's fourth slot), the epilogue walks the 32-feature chunks through four 4 KB staging boxes -- TMA load of
+      // the raw query box (L2: the UMMAs have just streamed it) two chunks ahead, finish in place, TMA store.
+      int gc = 0;   // chunk sequence number of this CTA: staging slot gc % 4, parity (gc / 4) & 1
+      auto stage_in = [&](int64_t pp, int c, int gcc) {   // lane 0: the slot's last store (chunk gcc - 4) has been read
+        mbar_arrive_expect_tx(&S->dqs_full[gcc % kDqSlots], (uint32_t)kQBoxBytes);
+        tma_load_3d(&tmap_q, dqs + (size_t)(gcc % kDqSlots) * kQBoxBytes, &S->dqs_full[gcc % kDqSlots], c * 32, 0, (int)pp, kEvictNormal);
+      };
       for (int64_t p = p_begin; p < p_end; ++p) {
-        const int pi = (int)(p - p_begin), qb = pi & 1;
+        const int pi = (int)(p - p_begin);
         const float rsq = P.saved[kp_saved_rsq_off(P.B, p, P.Ld) + lane];
+        if (lane == 0) {   // first two chunks on their way while the pair's last UMMAs finish
+          bulk_wait_group_read<0>();
+          stage_in(p, 0, gc);
+          if (nch > 1) stage_in(p, 1, gc + 1);
+        }
         KPB_T(0, mbar_wait<true>(&S->dq_full, (uint32_t)(pi & 1)));
         tc_fence_after_sync();
-        uint8_t* qtile = qbuf + (size_t)qb * qbuf_bytes;
         // q^_i . dq^_i: the four document-row quarters of this query row's half, fixed order
         const int w0 = (lane >> 4) * 4, x = lane & 15;
         const float(*cp)[16] = S->ci_part[pi & 3];
         const float cq = (cp[w0][x] + cp[w0 + 1][x]) + (cp[w0 + 2][x] + cp[w0 + 3][x]);
         const float s1 = rsq * P.tf32_comp;
         const float s2 = rsq * cq * (rsq < 1e12f ? rsq : 0.f);   // (q^_i . dq^_i) / |q_i|, times 1 / (|q_i| + eps)
-        for (int c = 0; c < nch; ++c) {
+        for (int c = 0; c < nch; ++c, ++gc) {
+          if (lane == 0 && c + 2 < nch) {
+            bulk_wait_group_read<1>();   // the store of chunk c - 2 (same slot as c + 2) has read its box; chunk c - 1's may be pending
+            stage_in(p, c + 2, gc + 2);
+          }
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + (uint32_t)(kColDq + 32 * c), r);
+          KPB_T(1, mbar_wait<true>(&S->dqs_full[gc % kDqSlots], (uint32_t)((gc / kDqSlots) & 1)));
           tmem_ld_wait();
+          uint8_t* box = dqs + (size_t)(gc % kDqSlots) * kQBoxBytes;
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
-            float4* cell = reinterpret_cast<float4*>(qtile + (size_t)c * kQBoxBytes + sw128x32_offset(lane, cc));
+            float4* cell = reinterpret_cast<float4*>(box + sw128x32_offset(lane, cc));
             const float4 qv = *cell;
             float4 o;
             o.x = fmaf(s1, __uint_as_float(r[4 * cc + 0]), -qv.x * s2);
@@ -582,22 +594,16 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
             o.w = fmaf(s1, __uint_as_float(r[4 * cc + 3]), -qv.w * s2);
             *cell = o;
           }
-          if ((c + 1) % stage_boxes == 0 || c == nch - 1) {   // the columns of stage c / stage_boxes are drained
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S->dq_empty[c / stage_boxes]);
+          tc_fence_before_sync();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if ((c + 1) % stage_boxes == 0 || c == nch - 1) mbar_arrive(&S->dq_empty[c / stage_boxes]);   // stage drained
+            tma_store_3d(&tmap_dq, box, c * 32, 0, (int)p);
+            bulk_commit_group();
           }
+          __syncwarp();
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          for (int c = 0; c < nch; ++c)
-            tma_store_3d(&tmap_dq, qbuf + (size_t)qb * qbuf_bytes + (size_t)c * kQBoxBytes, c * 32, 0, (int)p);
-          bulk_commit_group();
-          KPB_T(1, bulk_wait_group_read<0>());
-          mbar_arrive(&S->q_empty[qb]);
-        }
-        __syncwarp();
       }
       if (lane == 0) bulk_wait_group<0>();
     }
@@ -632,10 +638,10 @@ int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const 
            const CUtensorMap& tdq, const CUtensorMap& tdd) {
   constexpr int KBP = (KB + 3) & ~3;
   const int nch = (P.D + 31) / 32;
-  const size_t fixed = 1024 + 2 * (size_t)kG2Bytes + 2 * (size_t)nch * kQBoxBytes + sizeof(BwShared<KBP>);
+  const size_t fixed = 1024 + 2 * (size_t)kG2Bytes + (size_t)kDqSlots * kQBoxBytes + sizeof(BwShared<KBP>);
   int stage_boxes = kStageBoxes;
   if (const char* e = getenv("MMB200_KPB_BOXES")) stage_boxes = std::max(1, std::min(kStageBoxes, atoi(e)));
-  const size_t stage_bytes = (size_t)stage_boxes * kBoxBytes;
+  const size_t stage_bytes = (size_t)stage_boxes * (kBoxBytes + kQBoxBytes);
   int n_stages = std::min<int>(kMaxStages, (int)(((size_t)dev.max_smem_optin - fixed) / stage_bytes));
   if (const char* e = getenv("MMB200_KPB_STAGES")) n_stages = std::max(1, std::min(n_stages, atoi(e)));
   const int mn_sbo = 512;
