@@ -333,10 +333,10 @@ class KernelPoolTrainWorkload(KernelPoolWorkload):
     launches_per_step = 3   # forward (saves cosines + norms), tcgen05 backward, batch reduction of d weight / d alpha
     graph_ok = True         # torch.autograd inside the capture (forward + backward of the step, as in whole-step capture)
 
-    def __init__(self, rank, dev):
+    def __init__(self, rank, dev, pairs=1024):
         super().__init__(rank, dev, "tk")
         self.name = "tk_kernel_pool_train"
-        self.B = self.pairs = 1024
+        self.B = self.pairs = pairs   # <= the 4096 pairs of the forward workload
         self.q, self.d, self.qm, self.dm = self.q[:self.B], self.d[:self.B], self.qm[:self.B], self.dm[:self.B]
         self.metric = "query-doc pairs/sec (TK cosine + RBF kernel pooling forward + backward, D=300)"
         self.kernel = "kernel_pool_ts_kernel<save> + kernel_pool_bwd_tc_kernel"
@@ -739,6 +739,26 @@ def bench_secondary(name, dev, steps, cpu_budget_s):
                    "steps": n_e2e, "statistic": "median of per-step wall times", "note": wl.e2e_note}}
     if cpu_budget_s > 0:
         rec["cpu_baseline"] = time_cpu(wl, budget_s=cpu_budget_s, max_reps=10, one_thread_budget_s=0)
+    if name == "tk_train":
+        # the same step at the forward workload's batch (4096 pairs, 28 per SM instead of 7): the persistent kernels'
+        # prologue and the pair boundaries weigh less -- reported next to the 1024-pair figure, not instead of it
+        del wl
+        torch.cuda.empty_cache()
+        big = KernelPoolTrainWorkload(0, dev, pairs=4096)
+        big.to_device()
+        for _ in range(3):
+            big.kernel_step()
+        torch.cuda.synchronize()
+        bstep = graphed_step(big.kernel_step, dev) or big.kernel_step
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            bstep()
+        e1.record()
+        torch.cuda.synchronize()
+        bms = e0.elapsed_time(e1) / steps
+        rec["at_4096_pairs"] = {"value": big.pairs / (bms * 1e-3), "unit": "pairs/s", "ms_per_step": bms,
+                                "roofline_frac": _roofline(big, bms, name)["frac"]}
     return rec
 
 
