@@ -739,6 +739,27 @@ def bench_secondary(name, dev, steps, cpu_budget_s):
                    "steps": n_e2e, "statistic": "median of per-step wall times", "note": wl.e2e_note}}
     if cpu_budget_s > 0:
         rec["cpu_baseline"] = time_cpu(wl, budget_s=cpu_budget_s, max_reps=10, one_thread_budget_s=0)
+    if name == "tkl":
+        # the same step on four times as many documents: the three helper kernels around tkl_ts_kernel (slot map, tile plan,
+        # top hills: ~25 us, latency-bound, independent of the batch) weigh a quarter as much -- next to the 128-document
+        # figure, not instead of it
+        del wl
+        torch.cuda.empty_cache()
+        big = TklWorkload(0, dev, B=512)
+        big.to_device()
+        for _ in range(3):
+            big.kernel_step()
+        torch.cuda.synchronize()
+        bstep = graphed_step(big.kernel_step, dev) or big.kernel_step
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            bstep()
+        e1.record()
+        torch.cuda.synchronize()
+        bms = e0.elapsed_time(e1) / steps
+        rec["at_512_docs"] = {"value": big.pairs / (bms * 1e-3), "unit": "pairs/s", "ms_per_step": bms,
+                              "roofline_frac": _roofline(big, bms, name)["frac"]}
     if name == "tk_train":
         # the same step at the forward workload's batch (4096 pairs, 28 per SM instead of 7): the persistent kernels'
         # prologue and the pair boundaries weigh less -- reported next to the 1024-pair figure, not instead of it
