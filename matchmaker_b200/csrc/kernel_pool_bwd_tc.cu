@@ -237,7 +237,7 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       uint32_t ph = 0, aph = 0;
       int tseq = 0;
       for (int64_t p = p_begin; p < p_end; ++p) {
-        const int pi = (int)(p - p_begin), qb = pi & 1;
+        const int pi = (int)(p - p_begin);
         tc_fence_after_sync();
         for (int t = 0; t < tiles; ++t, ++tseq) {
           const int g = tseq & 1;
