@@ -212,12 +212,11 @@ kernel_pool_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         int slot = 0;
         uint32_t ph = 0;
         for (int64_t p = p_begin; p < p_end; ++p) {
-          const int pi = (int)(p - p_begin);
           for (int t = 0; t < tiles; ++t)
             for (int s = 0; s < spt; ++s) {
               const int nb = min(stage_boxes, nch - s * stage_boxes);
               KPB_T(1, mbar_wait<true>(&S->raw_empty[slot], ph ^ 1u));
-              KPB_TRACE(pi * tiles * spt + t * spt + s, 0);
+              KPB_TRACE((int)(p - p_begin) * tiles * spt + t * spt + s, 0);
               mbar_arrive_expect_tx(&S->raw_full[slot], (uint32_t)(nb * (kBoxBytes + kQBoxBytes)));
               for (int b = 0; b < nb; ++b) {
                 tma_load_3d(&tmap_d, ring + (size_t)slot * stage_bytes + (size_t)b * kBoxBytes, &S->raw_full[slot],
@@ -637,7 +636,6 @@ template <int KB, bool GATE>
 int launch(const KpParams& P, const DeviceInfo& dev, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& td,
            const CUtensorMap& tdq, const CUtensorMap& tdd) {
   constexpr int KBP = (KB + 3) & ~3;
-  const int nch = (P.D + 31) / 32;
   const size_t fixed = 1024 + 2 * (size_t)kG2Bytes + (size_t)kDqSlots * kQBoxBytes + sizeof(BwShared<KBP>);
   int stage_boxes = kStageBoxes;
   if (const char* e = getenv("MMB200_KPB_BOXES")) stage_boxes = std::max(1, std::min(kStageBoxes, atoi(e)));
