@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(1024) tkl_plan_kernel(const int32_t* __restric
   __shared__ int carry;
   __shared__ int total_tiles, total_cost;
   __shared__ float klo[32], khi[32];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // tkl_ts_kernel may start its prologue now (it waits for this grid's completion before it reads the plan)
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t < K && t < 32) {
     const float h = 11.0f * sigma[t] / sqrtf(0.5f * 1.4426950408889634f);
@@ -180,8 +181,12 @@ __global__ void __launch_bounds__(1024) tkl_plan_kernel(const int32_t* __restric
     khi[t] = mu[t] + h;
   }
   const int tiles_max = (C + kTileSlots - 1) / kTileSlots;
-  int32_t* tile_pre = plan + 2;
-  int32_t* cost_pre = plan + 3 + B;
+  // up to 1024 documents the two prefix arrays live in shared memory while they are built, scanned and searched (the global
+  // round trips of the scans and of the 150 binary searches were a third of this kernel's 15 us); written out once at the end
+  __shared__ int32_t s_tile[1025], s_cost[1025];
+  const bool in_smem = B <= 1024;
+  int32_t* tile_pre = in_smem ? s_tile : plan + 2;
+  int32_t* cost_pre = in_smem ? s_cost : plan + 3 + B;
   int32_t* cta_start = plan + 4 + 2 * B;
   // pass 1: tiles and cost of every document: one warp per document, four documents per warp in flight (all of their slot
   // and mask words are requested before the first ballot -- one global-memory latency per batch, not four per document)
@@ -248,20 +253,26 @@ __global__ void __launch_bounds__(1024) tkl_plan_kernel(const int32_t* __restric
     }
     cta_start[x] = start;
   }
+  if (in_smem)
+    for (int64_t i = t; i <= B; i += 1024) { plan[2 + i] = s_tile[i]; plan[3 + B + i] = s_cost[i]; }
+  // Cover: activation k is non-zero (ex2.approx.ftz) for |c - mu_k| * a_k <= sqrt(126); 11.0 leaves a margin.  The union of
+  // the intervals [klo, khi] covers [-1.01, 1.01] iff the left end and every right end inside the range lie inside an
+  // interval that extends beyond them -- one thread per end point instead of a serial sweep.
+  __shared__ int uncovered;
+  if (t == 0) uncovered = 0;
+  __syncthreads();
+  if (t <= K && t <= 32) {
+    const float x = t == 0 ? -1.01f : khi[t - 1];
+    if (x >= -1.01f && x < 1.01f) {
+      bool ok = false;
+      for (int k = 0; k < K; ++k) ok = ok || (klo[k] <= x && khi[k] > x);
+      if (!ok) atomicExch(&uncovered, 1);
+    }
+  }
+  __syncthreads();
   if (t == 0) {
     plan[1] = total_tiles;
-    // activation k is non-zero (ex2.approx.ftz) for |c - mu_k| * a_k <= sqrt(126); 11.0 leaves a margin.  Sweep the
-    // union of the intervals [klo, khi] (computed by K threads at the start) over [-1.01, 1.01].
-    float x = -1.01f;
-    bool ok = true;
-    while (x < 1.01f) {
-      float reach = x;
-      for (int k = 0; k < K; ++k)
-        if (klo[k] <= x && khi[k] > reach) reach = khi[k];
-      if (reach <= x) { ok = false; break; }
-      x = reach;
-    }
-    plan[0] = (ok || force_cover == 1) && force_cover != -1 ? 1 : 0;
+    plan[0] = (uncovered == 0 || force_cover == 1) && force_cover != -1 ? 1 : 0;
   }
 }
 
@@ -338,13 +349,6 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   const long long t_start = t_mark;
 #endif
   extern __shared__ uint8_t smem_raw[];
-  if (P.plan[0] != 1) {
-    if (!fallback_available && blockIdx.x == 0 && threadIdx.x == 0) {
-      printf("mmb200 tkl: kernel set does not cover the cosine range and the FFMA kernel cannot run this shape\n");
-      __trap();
-    }
-    return;
-  }
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* qring = smem;                                                    // [kOps][Qhi;Qlo]
   uint8_t* raws = smem + kOps * kQopBytes;                                  // [n_raw][Dx | Qx]
@@ -369,9 +373,18 @@ tkl_ts_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem_base = S->tmem_base;
 
+  // Programmatic dependent launch: this grid is launched while the plan kernel still runs (it triggers its dependents at
+  // its first instruction), so the launch latency and the prologue above overlap with it; everything below reads the plan.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const bool covered = P.plan[0] == 1;
+  if (!covered && !fallback_available && blockIdx.x == 0 && threadIdx.x == 0) {
+    printf("mmb200 tkl: kernel set does not cover the cosine range and the FFMA kernel cannot run this shape\n");
+    __trap();
+  }
+
   // every role walks the same tile sequence with its own copy of the iterator (set up inside the role branch, after
-  // setmaxnreg, so that it lives in that role's registers)
-#define TKL_WALK() TileWalk tw; const bool have_work = tw.init(P.plan, (int)P.B, (int)blockIdx.x, (int)gridDim.x)
+  // setmaxnreg, so that it lives in that role's registers); without cover nobody has work and the FFMA kernel takes over
+#define TKL_WALK() TileWalk tw; const bool have_work = covered && tw.init(P.plan, (int)P.B, (int)blockIdx.x, (int)gridDim.x)
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -897,12 +910,13 @@ int tkl_window_ts_launch(TklParams& P, const DeviceInfo& dev, cudaStream_t strea
 #ifdef MMB200_ENABLE_PROF
   if (const char* e = getenv("MMB200_TKL_COVER")) force = atoi(e);  // 1 / -1: force the answer of the cover test
 #endif
+  // the zero fill first: the window-score kernel is a programmatic dependent of the plan kernel (nothing may sit between them)
+  MMB_CHECK_CUDA(cudaMemsetAsync(P.window_score, 0, (size_t)P.B * P.W * sizeof(float), stream));
   tkl_plan_kernel<<<1, 1024, 0, stream>>>(P.slot_to_packed, P.q_mask, P.mask_dtype, P.B, P.C, P.Lq, P.mu, P.sigma, P.K, grid,
                                           force, plan);
   MMB_CHECK_CUDA(cudaGetLastError());
   P.plan = plan;
   *plan_out = plan;
-  MMB_CHECK_CUDA(cudaMemsetAsync(P.window_score, 0, (size_t)P.B * P.W * sizeof(float), stream));
   const int fallback = P.segs > 0 ? 1 : 0;
   long long* prof = nullptr;
 #ifdef MMB200_ENABLE_PROF
@@ -912,6 +926,19 @@ int tkl_window_ts_launch(TklParams& P, const DeviceInfo& dev, cudaStream_t strea
     MMB_CHECK_CUDA(cudaMemset(prof, 0, (45 + 4 * 160) * sizeof(long long)));
   }
 #endif
+  auto launch_pdl = [&](auto kernel) -> cudaError_t {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, tq, tc, P, n_raw, fallback, prof);
+  };
   static bool attr_set[2][64] = {};
   const int di = dev.device & 63;
   if (P.saturation == 0) {
@@ -919,13 +946,13 @@ int tkl_window_ts_launch(TklParams& P, const DeviceInfo& dev, cudaStream_t strea
       MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev.max_smem_optin));
       attr_set[0][di] = true;
     }
-    tkl_ts_kernel<0><<<grid, kThreads, smem, stream>>>(tq, tc, P, n_raw, fallback, prof);
+    MMB_CHECK_CUDA(launch_pdl(tkl_ts_kernel<0>));
   } else {
     if (!attr_set[1][di]) {
       MMB_CHECK_CUDA(cudaFuncSetAttribute(tkl_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev.max_smem_optin));
       attr_set[1][di] = true;
     }
-    tkl_ts_kernel<1><<<grid, kThreads, smem, stream>>>(tq, tc, P, n_raw, fallback, prof);
+    MMB_CHECK_CUDA(launch_pdl(tkl_ts_kernel<1>));
   }
   MMB_CHECK_CUDA(cudaGetLastError());
 #ifdef MMB200_ENABLE_PROF
