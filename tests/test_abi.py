@@ -75,3 +75,17 @@ def test_flat_ip_plan_invariants(sm_count):
                 assert ws >= nq * n_ranges * kpad * 12           # (score, id) candidates per query and range
     assert lib.mmb200_flat_ip_plan(0, 10, 1, sm_count, out) == _lib.ERR_INVALID
     assert lib.mmb200_flat_ip_plan(10, 10, 1025, sm_count, out) == _lib.ERR_INVALID
+
+
+def test_training_pair_envelope_and_saved_size():
+    """Host-side contract of the tensor-core training pair (pure arithmetic, no GPU): the envelope the Python layer routes
+    on, and the size of the opaque state the forward leaves for the backward."""
+    lib = _lib.load()
+    ok = lib.mmb200_kernel_pool_train_tc_supported
+    assert ok(30, 200, 300, 21) == 1 and ok(30, 180, 300, 11) == 1 and ok(32, 2000, 320, 32) == 1 and ok(1, 1, 4, 1) == 1
+    assert ok(33, 200, 300, 21) == 0      # more than 32 query terms: FFMA backward (the forward runs per 32-row block)
+    assert ok(30, 200, 324, 21) == 0      # the query-gradient accumulator holds 320 columns
+    assert ok(30, 200, 302, 21) == 0      # 16-byte rows
+    assert ok(30, 200, 300, 33) == 0
+    assert lib.mmb200_kernel_pool_saved_floats(7, 200) == 7 * (33 * 200 + 32)
+    assert lib.mmb200_kernel_pool_saved_floats(0, 200) == 0
