@@ -11,7 +11,8 @@
 //
 // This file is the fp32-exact FFMA implementation: one CTA per pair, the normalised query block
 // (32 rows) resident in shared memory, document rows streamed in tiles.  It serves every shape and is the
-// validated baseline for the tcgen05 forward kernel (kernel_pool_tc.cu).
+// validated baseline for the tensor-core kernels: forward kernel_pool_ts.cu, backward kernel_pool_bwd_tc.cu (the
+// training pair mmb200_kernel_pool_fwd_train / _bwd_saved below routes to them).
 #include <algorithm>
 
 #include <cstdlib>
